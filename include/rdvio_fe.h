@@ -1,0 +1,173 @@
+/*
+ * rdvio_fe.h -- C ABI of the B200-native rd_vio visual front-end (librdvio_fe.so).
+ *
+ * This is the drop-in boundary for ONE hot path of SummerSigh/rd_vio: the
+ * rdvio::Image plugin (reference: src/rdvio/include/rdvio/types.h:153-177) as
+ * implemented by rdvio::extra::OpenCvImage (src/rdvio_extra/src/opencv_image.cpp)
+ * and driven once per camera frame by FeatureTracker::run
+ * (src/rdvio/src/feature_tracker.cpp:26-111).  The reference has no FFI of its
+ * own (it calls OpenCV in-process); each entry point below states which
+ * reference member function it replaces.  include/rdvio_b200/gpu_image.hpp is
+ * the C++ Image subclass that forwards to these calls; INTEGRATION.md shows
+ * the one-line change at the construction site (rdvio.hpp:50-53).
+ *
+ * Conventions
+ *  - plain C types, caller-owned buffers, no exceptions across the ABI;
+ *  - every function returns 0 (RDFE_OK) on success, a negative rdfe_status
+ *    otherwise; rdfe_last_error() gives a thread-local message;
+ *  - "slot" = one image resident in HBM with its pyramid (what one OpenCvImage
+ *    instance holds between preprocess() and release_image_buffer());
+ *  - batched: every call takes n independent images (camera streams share no
+ *    state); n = 1 is the per-frame plugin case;
+ *  - keypoints are (x, y) pairs of doubles, the layout of
+ *    std::vector<Eigen::Matrix<double,2,1>> (types.h:55-59);
+ *  - *_dev variants take DEVICE pointers and only enqueue work on the context's
+ *    stream (no host synchronisation); the host variants copy in/out and
+ *    return when results are in the caller's buffers.
+ */
+#ifndef RDVIO_FE_H
+#define RDVIO_FE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RDFE_API __attribute__((visibility("default")))
+#else
+#define RDFE_API
+#endif
+
+#define RDFE_ABI_VERSION 1
+#define RDFE_MAX_LEVELS 8        /* pyramid images (maxLevel + 1) */
+#define RDFE_MAX_BATCH 128       /* images per batched call */
+
+typedef enum rdfe_status {
+    RDFE_OK = 0,
+    RDFE_ERR_INVALID = -1,       /* bad argument */
+    RDFE_ERR_CUDA = -2,          /* CUDA runtime/driver failure */
+    RDFE_ERR_NOMEM = -3,
+    RDFE_ERR_NOSLOT = -4,        /* slot pool exhausted */
+    RDFE_ERR_UNSUPPORTED = -5,   /* e.g. LK window other than 21 or 31 */
+    RDFE_ERR_OVERFLOW = -6       /* corner-candidate buffer overflow */
+} rdfe_status;
+
+typedef struct rdfe_ctx rdfe_ctx;
+
+typedef struct rdfe_config {
+    int device;        /* CUDA device ordinal */
+    int width;         /* level-0 image size (OpenCvImage::width()/height(), opencv_image.h:15-17) */
+    int height;
+    int max_level;     /* OpenCV maxLevel = Image::level_num() (3, opencv_image.h:19) => max_level+1 images */
+    int win;           /* LK window, Size(21,21) in the reference (opencv_image.cpp:96,159); 21 or 31 */
+    int num_slots;     /* images resident at once (>= 2 per stream: previous + new frame) */
+    int max_points;    /* capacity: keypoints per image per detect/track call */
+    void *stream;      /* optional cudaStream_t to run on (NULL: the context creates its own) */
+} rdfe_config;
+
+/* Harris/GFTT parameters of OpenCvImage::gftt (opencv_image.cpp:184-188):
+ * GFTTDetector::create(max_points, 1e-3, 20, 3, useHarrisDetector=true), k = 0.04. */
+typedef struct rdfe_detect_params {
+    int max_points;             /* maxCorners (feature_tracker_max_keypoint_detection, config.cpp:25) */
+    double quality_level;       /* 1e-3 */
+    double min_distance;        /* 20 (GFTT's own suppression radius) */
+    double harris_k;            /* 0.04 */
+    double keypoint_distance;   /* PoissonDiskFilter radius (feature_tracker_min_keypoint_distance, config.cpp:23) */
+    int border;                 /* 20-px border reject (opencv_image.cpp:61-68) */
+    int harris_fma;             /* 0: plain C++ float order (parity target); 1: FMA order of OpenCV's AVX2 dispatch */
+} rdfe_detect_params;
+
+/* LK parameters of OpenCvImage::track_keypoints (opencv_image.cpp:94-98,101-113,130). */
+typedef struct rdfe_track_params {
+    int max_count;              /* TermCriteria COUNT, 30 */
+    double epsilon;             /* TermCriteria EPS, 0.01 */
+    double min_eig_threshold;   /* calcOpticalFlowPyrLK default 1e-4 */
+    int border;                 /* 20-px border gate on the forward result */
+    double max_round_trip;      /* 0.5 px forward-backward gate */
+    int has_prediction;         /* 1: next_xy holds the caller's prediction (OPTFLOW_USE_INITIAL_FLOW seed);
+                                   0: seed with curr_xy (opencv_image.cpp:81-86) */
+} rdfe_track_params;
+
+RDFE_API const char *rdfe_last_error(void);
+RDFE_API int rdfe_abi_version(void);
+RDFE_API void rdfe_default_detect_params(rdfe_detect_params *p);
+RDFE_API void rdfe_default_track_params(rdfe_track_params *p);
+
+/* ---- context ------------------------------------------------------------ */
+RDFE_API int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out);
+RDFE_API void rdfe_destroy(rdfe_ctx *ctx);
+RDFE_API int rdfe_num_levels(const rdfe_ctx *ctx);                 /* images actually built (buildOpticalFlowPyramid may stop early) */
+RDFE_API int rdfe_level_size(const rdfe_ctx *ctx, int level, int *width, int *height);
+RDFE_API int rdfe_sync(rdfe_ctx *ctx);                             /* wait for everything enqueued on the context */
+RDFE_API void *rdfe_stream(rdfe_ctx *ctx);                         /* the cudaStream_t work is enqueued on */
+RDFE_API int64_t rdfe_kernel_launches(const rdfe_ctx *ctx);        /* kernels launched by this context so far */
+
+/* ---- slots: replace the cv::Mat members' lifetime ----------------------- */
+RDFE_API int rdfe_slot_acquire(rdfe_ctx *ctx, int *slot);          /* make_shared<OpenCvImage>() (rdvio.hpp:50) */
+RDFE_API int rdfe_slot_release(rdfe_ctx *ctx, int slot);           /* OpenCvImage::release_image_buffer (opencv_image.cpp:200-208) */
+
+/* ---- OpenCvImage::preprocess (opencv_image.cpp:156-161) ----------------- */
+/* CLAHE(clip_limit, tiles_x x tiles_y) in place, then the (max_level+1)-image
+ * pyramid with Scharr derivatives.  images[i] is the 8-bit gray frame for
+ * slots[i], `pitch` bytes per row. */
+RDFE_API int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n,
+                          const uint8_t *const *images, size_t pitch,
+                          double clip_limit, int tiles_x, int tiles_y);
+RDFE_API int rdfe_preprocess_batch_dev(rdfe_ctx *ctx, const int *slots, int n,
+                              const uint8_t *const *dev_images, size_t pitch,
+                              double clip_limit, int tiles_x, int tiles_y);
+
+/* ---- OpenCvImage::detect_keypoints (opencv_image.cpp:38-73) ------------- */
+/* keypoints_xy: [n][stride][2] doubles; counts[i] existing keypoints on entry
+ * (they preset the Poisson-disk filter), new ones are appended and counts[i]
+ * updated (never beyond `stride`).  gftt_* (optional, may be NULL) receive the
+ * raw GFTT corners [n][max_points][2] float, responses, and counts. */
+RDFE_API int rdfe_detect_batch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p,
+                      double *keypoints_xy, int *counts, int stride,
+                      float *gftt_xy, float *gftt_resp, int *gftt_counts);
+RDFE_API int rdfe_detect_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p,
+                          double *dev_keypoints_xy, int *dev_counts, int stride,
+                          float *dev_gftt_xy, float *dev_gftt_resp, int *dev_gftt_counts);
+
+/* ---- OpenCvImage::track_keypoints (opencv_image.cpp:75-154) ------------- */
+/* Forward pyramidal LK curr->next, border/jump gating, backward LK, 0.5-px
+ * round-trip gate, all in one launch.  curr_xy, next_xy: [n][stride][2]
+ * doubles; counts[i] points for image i; status: [n][stride] chars in {0,1}.
+ * next_xy is in/out: prediction in (if has_prediction), result out, and only
+ * entries with status != 0 are overwritten (opencv_image.cpp:148-153). */
+RDFE_API int rdfe_track_batch(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots, int n,
+                     const rdfe_track_params *p, const double *curr_xy, double *next_xy,
+                     const int *counts, int stride, char *status);
+RDFE_API int rdfe_track_batch_dev(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots, int n,
+                         const rdfe_track_params *p, const double *dev_curr_xy, double *dev_next_xy,
+                         const int *dev_counts, int stride, char *dev_status);
+
+/* ---- parity / debugging taps (not on the hot path) ---------------------- */
+/* plane: 0 = 8-bit image (w*h bytes), 1 = Scharr derivative (w*h*2 int16),
+ * 2 = image with its win-px REFLECT_101 halo ((w+2win)*(h+2win) bytes). */
+RDFE_API int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst, size_t dst_bytes);
+RDFE_API int rdfe_download_clahe_lut(rdfe_ctx *ctx, int batch_index, uint8_t *dst, size_t dst_bytes);
+/* Harris response map of the slot's level-0 image (w*h floats). */
+RDFE_API int rdfe_harris_response(rdfe_ctx *ctx, int slot, const rdfe_detect_params *p, float *dst, size_t dst_bytes);
+
+/* ---- device-buffer helpers for callers without a CUDA runtime binding --- */
+RDFE_API int rdfe_dev_alloc(rdfe_ctx *ctx, size_t bytes, void **dev_ptr);
+RDFE_API int rdfe_dev_free(rdfe_ctx *ctx, void *dev_ptr);
+RDFE_API int rdfe_host_alloc(rdfe_ctx *ctx, size_t bytes, void **host_ptr);     /* pinned */
+RDFE_API int rdfe_host_free(rdfe_ctx *ctx, void *host_ptr);
+RDFE_API int rdfe_memcpy_h2d(rdfe_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes, int async);
+RDFE_API int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes, int async);
+
+/* CUDA-event timing on the context's stream: start/stop bracket enqueued work,
+ * elapsed_ms synchronises on the stop event. */
+RDFE_API int rdfe_timer_start(rdfe_ctx *ctx);
+RDFE_API int rdfe_timer_stop(rdfe_ctx *ctx);
+RDFE_API int rdfe_timer_elapsed_ms(rdfe_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDVIO_FE_H */

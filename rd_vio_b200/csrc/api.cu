@@ -1,0 +1,582 @@
+// api.cu -- the C ABI of librdvio_fe.so (see include/rdvio_fe.h for the contract and the
+// reference member functions each entry point replaces).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include "fe_internal.cuh"
+
+namespace rdfe {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_tensor_maps(rdfe_ctx *ctx) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return RDFE_ERR_CUDA; }
+    const Pyramid &pyr = ctx->pyr;
+    const int win = pyr.win;
+    const cuuint32_t jw = win == 21 ? 32 : 48, jh = jw;
+    const cuuint32_t dw = win == 21 ? 24 : 32, dh = win == 21 ? 22 : 32;
+    for (int l = 0; l < pyr.nlevels; ++l) {
+        const LevelGeom &g = pyr.lv[l];
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.ph, (cuuint64_t)ctx->cfg.num_slots};
+            cuuint64_t strides[2] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.islot};
+            cuuint32_t box[3] = {jw, jh, 1};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult r = enc(&ctx->tm_img[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr.img[l], dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image level %d) failed: %d", l, (int)r); return RDFE_ERR_CUDA; }
+        }
+        {
+            // derivative plane: one uint32 element = (dx, dy) int16 pair; dims are the true
+            // image size so that out-of-bounds reads return the reference's zero halo
+            cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)ctx->cfg.num_slots};
+            cuuint64_t strides[2] = {(cuuint64_t)g.dpitch, (cuuint64_t)g.dslot};
+            cuuint32_t box[3] = {dw, dh, 1};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult r = enc(&ctx->tm_der[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pyr.der[l], dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(deriv level %d) failed: %d", l, (int)r); return RDFE_ERR_CUDA; }
+        }
+    }
+    return RDFE_OK;
+}
+
+// CLAHE parameters exactly as cv::CLAHE_Impl::apply derives them
+static int make_clahe_params(const rdfe_ctx *ctx, double clip_limit, int tiles_x, int tiles_y, ClaheParams *cp) {
+    const int W = ctx->cfg.width, H = ctx->cfg.height;
+    if (tiles_x < 1 || tiles_y < 1 || tiles_x > kMaxTiles || tiles_y > kMaxTiles) {
+        set_error("CLAHE tile grid %dx%d out of range [1,%d]", tiles_x, tiles_y, kMaxTiles);
+        return RDFE_ERR_INVALID;
+    }
+    int PW = W, PH = H;
+    cp->padded = 0;
+    if (W % tiles_x != 0 || H % tiles_y != 0) {
+        PW = W + (tiles_x - (W % tiles_x));
+        PH = H + (tiles_y - (H % tiles_y));
+        cp->padded = 1;
+    }
+    cp->W = W; cp->H = H;
+    cp->tiles_x = tiles_x; cp->tiles_y = tiles_y;
+    cp->tw = PW / tiles_x; cp->th = PH / tiles_y;
+    const int area = cp->tw * cp->th;
+    cp->clip = 0;
+    if (clip_limit > 0.0) {
+        cp->clip = (int)(clip_limit * area / 256);
+        if (cp->clip < 1) cp->clip = 1;
+    }
+    cp->lut_scale = (float)255 / (float)area;
+    cp->inv_tw = 1.0f / (float)cp->tw;
+    cp->inv_th = 1.0f / (float)cp->th;
+    // interpolation cells: cell c <=> floor(x * inv_tw - 0.5f) + 1 == c  (monotone in x)
+    auto build = [](int n, int tiles, float inv, int *bnd) {
+        int c = 0;
+        bnd[0] = 0;
+        for (int x = 0; x < n; ++x) {
+            volatile float t = (float)x * inv;       // volatile: keep the two roundings separate
+            const float tf = t - 0.5f;
+            int cell = (int)floorf(tf) + 1;
+            if (cell > tiles) cell = tiles;            // cannot happen for in-range x; defensive
+            while (c < cell) bnd[++c] = x;
+        }
+        while (c < tiles + 1) bnd[++c] = n;
+    };
+    build(W, tiles_x, cp->inv_tw, cp->xb);
+    build(H, tiles_y, cp->inv_th, cp->yb);
+    return RDFE_OK;
+}
+
+static int check_slots(const rdfe_ctx *ctx, const int *slots, int n, SlotList *out, const char *what) {
+    if (!ctx || !slots || n < 1 || n > RDFE_MAX_BATCH) {
+        set_error("%s: batch size %d out of range [1,%d]", what, n, RDFE_MAX_BATCH);
+        return RDFE_ERR_INVALID;
+    }
+    out->n = n;
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= ctx->cfg.num_slots || !ctx->slot_used[slots[i]]) {
+            set_error("%s: slot %d (index %d) is not an acquired slot", what, slots[i], i);
+            return RDFE_ERR_INVALID;
+        }
+        out->v[i] = slots[i];
+    }
+    return RDFE_OK;
+}
+
+static int check_launch(rdfe_ctx *ctx, int launched, const char *what) {
+    if (launched < 0) return launched;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+        return RDFE_ERR_CUDA;
+    }
+    ctx->launches += launched;
+    return RDFE_OK;
+}
+
+}  // namespace rdfe
+
+using namespace rdfe;
+
+extern "C" {
+
+const char *rdfe_last_error(void) { return g_err; }
+int rdfe_abi_version(void) { return RDFE_ABI_VERSION; }
+
+void rdfe_default_detect_params(rdfe_detect_params *p) {
+    p->max_points = 150;
+    p->quality_level = 1.0e-3;
+    p->min_distance = 20.0;
+    p->harris_k = 0.04;
+    p->keypoint_distance = 20.0;
+    p->border = 20;
+    p->harris_fma = 0;
+}
+
+void rdfe_default_track_params(rdfe_track_params *p) {
+    p->max_count = 30;
+    p->epsilon = 0.01;
+    p->min_eig_threshold = 1e-4;
+    p->border = 20;
+    p->max_round_trip = 0.5;
+    p->has_prediction = 1;
+}
+
+int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
+    if (!cfg || !out) { set_error("rdfe_create: null argument"); return RDFE_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->width > 16384 || cfg->height > 16384) {
+        set_error("rdfe_create: image size %dx%d unsupported", cfg->width, cfg->height);
+        return RDFE_ERR_INVALID;
+    }
+    if (cfg->win != 21 && cfg->win != 31) {
+        set_error("rdfe_create: LK window %d unsupported (21 or 31)", cfg->win);
+        return RDFE_ERR_UNSUPPORTED;
+    }
+    if (cfg->max_level < 0 || cfg->max_level >= RDFE_MAX_LEVELS || cfg->num_slots < 1 || cfg->max_points < 1 ||
+        cfg->max_points > 8192) {
+        set_error("rdfe_create: max_level=%d num_slots=%d max_points=%d out of range", cfg->max_level, cfg->num_slots,
+                  cfg->max_points);
+        return RDFE_ERR_INVALID;
+    }
+    int ndev = 0;
+    RDFE_CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        set_error("rdfe_create: device %d not present (%d CUDA devices)", cfg->device, ndev);
+        return RDFE_ERR_INVALID;
+    }
+    RDFE_CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    RDFE_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_error("rdfe_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
+                  prop.major, prop.minor);
+        return RDFE_ERR_UNSUPPORTED;
+    }
+
+    rdfe_ctx *ctx = new rdfe_ctx();
+    memset(ctx, 0, sizeof *ctx);
+    ctx->cfg = *cfg;
+    Pyramid &pyr = ctx->pyr;
+    pyr.win = cfg->win;
+    // levels: buildOpticalFlowPyramid stops when the next level would be <= win
+    int w = cfg->width, h = cfg->height;
+    for (int l = 0; l <= cfg->max_level; ++l) {
+        LevelGeom &g = pyr.lv[l];
+        g.w = w; g.h = h;
+        g.ipitch = (int)align_up((size_t)w + 2 * kHaloX, 64);
+        g.ph = h + 2 * cfg->win;
+        g.islot = align_up((size_t)g.ipitch * g.ph, 256);
+        g.dpitch = (int)align_up((size_t)w * 4, 64);
+        g.dslot = align_up((size_t)g.dpitch * h, 256);
+        pyr.nlevels = l + 1;
+        const int nw = (w + 1) / 2, nh = (h + 1) / 2;
+        if (nw <= cfg->win || nh <= cfg->win) break;
+        w = nw; h = nh;
+    }
+    auto fail = [&](int rc) { rdfe_destroy(ctx); return rc; };
+#define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(e__)); return fail(RDFE_ERR_CUDA); } } while (0)
+    for (int l = 0; l < pyr.nlevels; ++l) {
+        CK(cudaMalloc(&pyr.img[l], pyr.lv[l].islot * cfg->num_slots));
+        CK(cudaMemset(pyr.img[l], 0, pyr.lv[l].islot * cfg->num_slots));
+        CK(cudaMalloc(&pyr.der[l], pyr.lv[l].dslot * cfg->num_slots));
+        CK(cudaMemset(pyr.der[l], 0, pyr.lv[l].dslot * cfg->num_slots));
+    }
+    ctx->raw_pitch = align_up((size_t)cfg->width, 64);
+    ctx->raw_slot = ctx->raw_pitch * cfg->height;
+    CK(cudaMalloc(&ctx->raw, ctx->raw_slot * cfg->num_slots));
+    CK(cudaMalloc(&ctx->lut, (size_t)RDFE_MAX_BATCH * kMaxTiles * kMaxTiles * 256));
+    ctx->det.cand_cap = (unsigned)((size_t)cfg->width * cfg->height / 2);
+    CK(cudaMalloc(&ctx->det.cand, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det.cand_count, RDFE_MAX_BATCH * sizeof(unsigned)));
+    CK(cudaMalloc(&ctx->det.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
+    CK(cudaMalloc(&ctx->det.overflow, sizeof(unsigned)));
+    CK(cudaMemset(ctx->det.overflow, 0, sizeof(unsigned)));
+    const size_t npts = (size_t)RDFE_MAX_BATCH * cfg->max_points;
+    CK(cudaMalloc(&ctx->d_xy_a, npts * 2 * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_xy_b, npts * 2 * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_counts, RDFE_MAX_BATCH * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_status, npts));
+    CK(cudaMalloc(&ctx->d_gftt_xy, npts * 2 * sizeof(float)));
+    CK(cudaMalloc(&ctx->d_gftt_resp, npts * sizeof(float)));
+    CK(cudaMalloc(&ctx->d_gftt_counts, RDFE_MAX_BATCH * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_srcptrs, RDFE_MAX_BATCH * sizeof(uint8_t *)));
+    if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
+    else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    CK(cudaEventCreate(&ctx->ev_t0));
+    CK(cudaEventCreate(&ctx->ev_t1));
+#undef CK
+    ctx->slot_used = (uint8_t *)calloc((size_t)cfg->num_slots, 1);
+    int rc = make_tensor_maps(ctx);
+    if (rc != RDFE_OK) return fail(rc);
+    *out = ctx;
+    return RDFE_OK;
+}
+
+void rdfe_destroy(rdfe_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int l = 0; l < RDFE_MAX_LEVELS; ++l) { cudaFree(ctx->pyr.img[l]); cudaFree(ctx->pyr.der[l]); }
+    cudaFree(ctx->raw); cudaFree(ctx->lut);
+    cudaFree(ctx->det.cand); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.overflow);
+    cudaFree(ctx->d_xy_a); cudaFree(ctx->d_xy_b); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
+    cudaFree(ctx->d_gftt_xy); cudaFree(ctx->d_gftt_resp); cudaFree(ctx->d_gftt_counts); cudaFree(ctx->d_srcptrs);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    free(ctx->slot_used);
+    delete ctx;
+}
+
+int rdfe_num_levels(const rdfe_ctx *ctx) { return ctx ? ctx->pyr.nlevels : RDFE_ERR_INVALID; }
+
+int rdfe_level_size(const rdfe_ctx *ctx, int level, int *width, int *height) {
+    if (!ctx || level < 0 || level >= ctx->pyr.nlevels) { set_error("rdfe_level_size: bad level %d", level); return RDFE_ERR_INVALID; }
+    if (width) *width = ctx->pyr.lv[level].w;
+    if (height) *height = ctx->pyr.lv[level].h;
+    return RDFE_OK;
+}
+
+int rdfe_sync(rdfe_ctx *ctx) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    unsigned ovf = 0;
+    RDFE_CUDA_OK(cudaMemcpy(&ovf, ctx->det.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
+    if (ovf) {
+        cudaMemset(ctx->det.overflow, 0, sizeof(unsigned));
+        set_error("corner-candidate buffer overflow (more than %u local maxima in one image)", ctx->det.cand_cap);
+        return RDFE_ERR_OVERFLOW;
+    }
+    return RDFE_OK;
+}
+
+void *rdfe_stream(rdfe_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int64_t rdfe_kernel_launches(const rdfe_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rdfe_slot_acquire(rdfe_ctx *ctx, int *slot) {
+    if (!ctx || !slot) return RDFE_ERR_INVALID;
+    for (int i = 0; i < ctx->cfg.num_slots; ++i)
+        if (!ctx->slot_used[i]) { ctx->slot_used[i] = 1; *slot = i; return RDFE_OK; }
+    set_error("rdfe_slot_acquire: all %d slots in use", ctx->cfg.num_slots);
+    return RDFE_ERR_NOSLOT;
+}
+
+int rdfe_slot_release(rdfe_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= ctx->cfg.num_slots || !ctx->slot_used[slot]) {
+        set_error("rdfe_slot_release: slot %d not acquired", slot);
+        return RDFE_ERR_INVALID;
+    }
+    ctx->slot_used[slot] = 0;
+    return RDFE_OK;
+}
+
+// ------------------------------------------------------------- preprocess
+int rdfe_preprocess_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *const *dev_images, size_t pitch,
+                              double clip_limit, int tiles_x, int tiles_y) {
+    SlotList sl;
+    int rc = check_slots(ctx, slots, n, &sl, "rdfe_preprocess_batch_dev");
+    if (rc) return rc;
+    if (!dev_images || pitch < (size_t)ctx->cfg.width) { set_error("rdfe_preprocess_batch_dev: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
+    ClaheParams cp;
+    rc = make_clahe_params(ctx, clip_limit, tiles_x, tiles_y, &cp);
+    if (rc) return rc;
+    int vec4 = (pitch % 4 == 0) ? 1 : 0;
+    for (int i = 0; i < n; ++i) {
+        if (!dev_images[i]) { set_error("rdfe_preprocess_batch_dev: image %d is null", i); return RDFE_ERR_INVALID; }
+        if ((uintptr_t)dev_images[i] % 4) vec4 = 0;
+    }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->last_clahe_tiles = tiles_x * tiles_y;
+    rc = check_launch(ctx, launch_clahe(ctx, sl, ctx->d_srcptrs, pitch, vec4, cp), "clahe");
+    if (rc) return rc;
+    return check_launch(ctx, launch_pyramid(ctx, sl), "pyramid");
+}
+
+int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *const *images, size_t pitch,
+                          double clip_limit, int tiles_x, int tiles_y) {
+    SlotList sl;
+    int rc = check_slots(ctx, slots, n, &sl, "rdfe_preprocess_batch");
+    if (rc) return rc;
+    if (!images || pitch < (size_t)ctx->cfg.width) { set_error("rdfe_preprocess_batch: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    std::vector<const uint8_t *> dptr(n);
+    for (int i = 0; i < n; ++i) {
+        if (!images[i]) { set_error("rdfe_preprocess_batch: image %d is null", i); return RDFE_ERR_INVALID; }
+        uint8_t *d = ctx->raw + (size_t)slots[i] * ctx->raw_slot;
+        RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width, (size_t)ctx->cfg.height,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        dptr[i] = d;
+    }
+    rc = rdfe_preprocess_batch_dev(ctx, slots, n, dptr.data(), ctx->raw_pitch, clip_limit, tiles_x, tiles_y);
+    if (rc) return rc;
+    return rdfe_sync(ctx);
+}
+
+// ----------------------------------------------------------------- detect
+static int check_detect(const rdfe_ctx *ctx, const rdfe_detect_params *p, int stride, const char *what) {
+    if (!p || p->max_points < 1 || p->max_points > ctx->cfg.max_points || stride < 1) {
+        set_error("%s: max_points=%d (capacity %d) stride=%d invalid", what, p ? p->max_points : -1, ctx->cfg.max_points, stride);
+        return RDFE_ERR_INVALID;
+    }
+    if (!(p->quality_level > 0) || p->min_distance < 0 || !(p->keypoint_distance > 0)) {
+        set_error("%s: quality_level/min_distance/keypoint_distance invalid", what);
+        return RDFE_ERR_INVALID;
+    }
+    return RDFE_OK;
+}
+
+int rdfe_detect_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p, double *dev_keypoints_xy,
+                          int *dev_counts, int stride, float *dev_gftt_xy, float *dev_gftt_resp, int *dev_gftt_counts) {
+    SlotList sl;
+    int rc = check_slots(ctx, slots, n, &sl, "rdfe_detect_batch_dev");
+    if (rc) return rc;
+    rc = check_detect(ctx, p, stride, "rdfe_detect_batch_dev");
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    rc = check_launch(ctx, launch_harris_candidates(ctx, sl, *p, nullptr), "harris");
+    if (rc) return rc;
+    return check_launch(ctx, launch_select(ctx, sl, *p, dev_keypoints_xy, dev_counts, stride, dev_gftt_xy, dev_gftt_resp,
+                                           dev_gftt_counts), "select");
+}
+
+int rdfe_detect_batch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p, double *keypoints_xy, int *counts,
+                      int stride, float *gftt_xy, float *gftt_resp, int *gftt_counts) {
+    if (!ctx || !keypoints_xy || !counts) { set_error("rdfe_detect_batch: null argument"); return RDFE_ERR_INVALID; }
+    if (n < 1 || n > RDFE_MAX_BATCH || stride < 1 || stride > ctx->cfg.max_points) {
+        set_error("rdfe_detect_batch: n=%d stride=%d out of range (capacity %d)", n, stride, ctx->cfg.max_points);
+        return RDFE_ERR_INVALID;
+    }
+    for (int i = 0; i < n; ++i)
+        if (counts[i] < 0 || counts[i] > stride) { set_error("rdfe_detect_batch: counts[%d]=%d out of range", i, counts[i]); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    const size_t xyb = (size_t)n * stride * 2 * sizeof(double);
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_xy_a, keypoints_xy, xyb, cudaMemcpyHostToDevice, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_counts, counts, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = rdfe_detect_batch_dev(ctx, slots, n, p, ctx->d_xy_a, ctx->d_counts, stride, gftt_xy ? ctx->d_gftt_xy : nullptr,
+                                   gftt_resp ? ctx->d_gftt_resp : nullptr, gftt_counts ? ctx->d_gftt_counts : nullptr);
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaMemcpyAsync(keypoints_xy, ctx->d_xy_a, xyb, cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(counts, ctx->d_counts, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t k = (size_t)p->max_points;
+    if (gftt_xy) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_xy, ctx->d_gftt_xy, n * k * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (gftt_resp) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_resp, ctx->d_gftt_resp, n * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (gftt_counts) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_counts, ctx->d_gftt_counts, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return rdfe_sync(ctx);
+}
+
+// ------------------------------------------------------------------ track
+int rdfe_track_batch_dev(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots, int n, const rdfe_track_params *p,
+                         const double *dev_curr_xy, double *dev_next_xy, const int *dev_counts, int stride, char *dev_status) {
+    SlotList sc, sn;
+    int rc = check_slots(ctx, curr_slots, n, &sc, "rdfe_track_batch_dev(curr)");
+    if (rc) return rc;
+    rc = check_slots(ctx, next_slots, n, &sn, "rdfe_track_batch_dev(next)");
+    if (rc) return rc;
+    if (!p || !dev_curr_xy || !dev_next_xy || !dev_counts || !dev_status || stride < 1) {
+        set_error("rdfe_track_batch_dev: null argument or stride < 1");
+        return RDFE_ERR_INVALID;
+    }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    return check_launch(ctx, launch_lk(ctx, sc, sn, *p, dev_curr_xy, dev_next_xy, dev_counts, stride, dev_status), "lk");
+}
+
+int rdfe_track_batch(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots, int n, const rdfe_track_params *p,
+                     const double *curr_xy, double *next_xy, const int *counts, int stride, char *status) {
+    if (!ctx || !curr_xy || !next_xy || !counts || !status || !p) { set_error("rdfe_track_batch: null argument"); return RDFE_ERR_INVALID; }
+    if (n < 1 || n > RDFE_MAX_BATCH || stride < 1 || stride > ctx->cfg.max_points) {
+        set_error("rdfe_track_batch: n=%d stride=%d out of range (capacity %d)", n, stride, ctx->cfg.max_points);
+        return RDFE_ERR_INVALID;
+    }
+    for (int i = 0; i < n; ++i)
+        if (counts[i] < 0 || counts[i] > stride) { set_error("rdfe_track_batch: counts[%d]=%d out of range", i, counts[i]); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    const size_t xyb = (size_t)n * stride * 2 * sizeof(double);
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_xy_a, curr_xy, xyb, cudaMemcpyHostToDevice, ctx->stream));
+    if (p->has_prediction) RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_xy_b, next_xy, xyb, cudaMemcpyHostToDevice, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_counts, counts, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RDFE_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, (size_t)n * stride, ctx->stream));
+    int rc = rdfe_track_batch_dev(ctx, curr_slots, next_slots, n, p, ctx->d_xy_a, ctx->d_xy_b, ctx->d_counts, stride, ctx->d_status);
+    if (rc) return rc;
+    // only status != 0 entries of next_xy may change (opencv_image.cpp:148-153): merge on the host
+    std::vector<double> tmp((size_t)n * stride * 2);
+    RDFE_CUDA_OK(cudaMemcpyAsync(tmp.data(), ctx->d_xy_b, xyb, cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(status, ctx->d_status, (size_t)n * stride, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = rdfe_sync(ctx);
+    if (rc) return rc;
+    for (int b = 0; b < n; ++b)
+        for (int i = 0; i < counts[b]; ++i) {
+            const size_t k = (size_t)b * stride + i;
+            if (status[k]) { next_xy[2 * k] = tmp[2 * k]; next_xy[2 * k + 1] = tmp[2 * k + 1]; }
+        }
+    return RDFE_OK;
+}
+
+// ------------------------------------------------------------ parity taps
+int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst, size_t dst_bytes) {
+    if (!ctx || !dst || slot < 0 || slot >= ctx->cfg.num_slots || level < 0 || level >= ctx->pyr.nlevels) {
+        set_error("rdfe_download_level: bad slot/level");
+        return RDFE_ERR_INVALID;
+    }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    const LevelGeom &g = ctx->pyr.lv[level];
+    const int win = ctx->pyr.win;
+    if (plane == 0) {
+        if (dst_bytes < (size_t)g.w * g.h) { set_error("rdfe_download_level: buffer too small"); return RDFE_ERR_INVALID; }
+        RDFE_CUDA_OK(cudaMemcpy2D(dst, g.w, ctx->pyr.image_origin(level, slot), g.ipitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    } else if (plane == 1) {
+        if (dst_bytes < (size_t)g.w * g.h * 4) { set_error("rdfe_download_level: buffer too small"); return RDFE_ERR_INVALID; }
+        RDFE_CUDA_OK(cudaMemcpy2D(dst, (size_t)g.w * 4, ctx->pyr.deriv_origin(level, slot), g.dpitch, (size_t)g.w * 4, g.h, cudaMemcpyDeviceToHost));
+    } else if (plane == 2) {
+        const size_t fw = (size_t)g.w + 2 * win, fh = (size_t)g.h + 2 * win;
+        if (dst_bytes < fw * fh) { set_error("rdfe_download_level: buffer too small"); return RDFE_ERR_INVALID; }
+        const uint8_t *src = ctx->pyr.image_origin(level, slot) - (size_t)win * g.ipitch - win;
+        RDFE_CUDA_OK(cudaMemcpy2D(dst, fw, src, g.ipitch, fw, fh, cudaMemcpyDeviceToHost));
+    } else {
+        set_error("rdfe_download_level: plane %d unknown", plane);
+        return RDFE_ERR_INVALID;
+    }
+    return RDFE_OK;
+}
+
+int rdfe_download_clahe_lut(rdfe_ctx *ctx, int batch_index, uint8_t *dst, size_t dst_bytes) {
+    if (!ctx || !dst || batch_index < 0 || batch_index >= RDFE_MAX_BATCH || ctx->last_clahe_tiles <= 0) {
+        set_error("rdfe_download_clahe_lut: bad argument or no preprocess yet");
+        return RDFE_ERR_INVALID;
+    }
+    const size_t bytes = (size_t)ctx->last_clahe_tiles * 256;
+    if (dst_bytes < bytes) { set_error("rdfe_download_clahe_lut: buffer too small"); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpy(dst, ctx->lut + (size_t)batch_index * bytes, bytes, cudaMemcpyDeviceToHost));
+    return RDFE_OK;
+}
+
+int rdfe_harris_response(rdfe_ctx *ctx, int slot, const rdfe_detect_params *p, float *dst, size_t dst_bytes) {
+    SlotList sl;
+    int rc = check_slots(ctx, &slot, 1, &sl, "rdfe_harris_response");
+    if (rc) return rc;
+    const size_t bytes = (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float);
+    if (!p || !dst || dst_bytes < bytes) { set_error("rdfe_harris_response: bad argument"); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    float *d = nullptr;
+    RDFE_CUDA_OK(cudaMalloc(&d, bytes));
+    rc = check_launch(ctx, launch_harris_candidates(ctx, sl, *p, d), "harris");
+    if (rc == RDFE_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(dst, d, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("rdfe_harris_response: %s", cudaGetErrorString(e)); rc = RDFE_ERR_CUDA; }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+// ---------------------------------------------------------- memory helpers
+int rdfe_dev_alloc(rdfe_ctx *ctx, size_t bytes, void **dev_ptr) {
+    if (!ctx || !dev_ptr) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaMalloc(dev_ptr, bytes));
+    return RDFE_OK;
+}
+int rdfe_dev_free(rdfe_ctx *ctx, void *dev_ptr) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaFree(dev_ptr));
+    return RDFE_OK;
+}
+int rdfe_host_alloc(rdfe_ctx *ctx, size_t bytes, void **host_ptr) {
+    if (!ctx || !host_ptr) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaMallocHost(host_ptr, bytes));
+    return RDFE_OK;
+}
+int rdfe_host_free(rdfe_ctx *ctx, void *host_ptr) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaFreeHost(host_ptr));
+    return RDFE_OK;
+}
+int rdfe_memcpy_h2d(rdfe_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes, int async) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!async) RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return RDFE_OK;
+}
+int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes, int async) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!async) RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return RDFE_OK;
+}
+
+int rdfe_timer_start(rdfe_ctx *ctx) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return RDFE_OK;
+}
+int rdfe_timer_stop(rdfe_ctx *ctx) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    return RDFE_OK;
+}
+int rdfe_timer_elapsed_ms(rdfe_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaEventSynchronize(ctx->ev_t1));
+    RDFE_CUDA_OK(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return RDFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// clahe.cu -- K1: CLAHE for 8-bit images, bit-exact with cv::CLAHE::apply
+// (reference call site: OpenCvImage::preprocess, src/rdvio_extra/src/opencv_image.cpp:157;
+//  parameters: OpenCvImage::clahe, :179-182; arithmetic: SURVEY.md App. A1).
+//
+// Two launches per batch:
+//   clahe_hist_lut_kernel  one CTA per (tile, image): 256-bin histogram with
+//                          per-warp private copies in shared memory, integer
+//                          clip + redistribute, prefix sum, LUT (float scale,
+//                          round-half-even).            HBM: reads S bytes.
+//   clahe_apply_kernel     one CTA per (row band, image): builds, per
+//                          interpolation cell column, a 256-entry table of
+//                          the FOUR tile-LUT bytes a pixel needs packed in one
+//                          32-bit word (one shared-memory gather per pixel
+//                          instead of four), then blends in float32 in the
+//                          reference's exact op order (no FMA) and writes
+//                          level 0 of the pyramid.      HBM: reads S, writes S.
+#include "fe_internal.cuh"
+
+namespace rdfe {
+
+constexpr int kHistWarps = 8;
+
+__global__ void __launch_bounds__(kHistWarps * 32)
+clahe_hist_lut_kernel(const uint8_t *const *__restrict__ src, size_t pitch, ClaheParams cp,
+                      uint8_t *__restrict__ lut) {
+    __shared__ unsigned hist[kHistWarps][256];
+    __shared__ unsigned wsum[kHistWarps];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
+    const uint8_t *img = src[b];
+
+    for (int i = tid; i < kHistWarps * 256; i += kHistWarps * 32) (&hist[0][0])[i] = 0u;
+    __syncthreads();
+
+    const int x0 = tx * cp.tw, y0 = ty * cp.th;
+    if (!cp.padded) {
+        for (int y = warp; y < cp.th; y += kHistWarps) {
+            const uint8_t *row = img + (size_t)(y0 + y) * pitch + x0;
+            for (int x = lane; x < cp.tw; x += 32) atomicAdd(&hist[warp][__ldg(row + x)], 1u);
+        }
+    } else {
+        // copyMakeBorder(..., BORDER_REFLECT_101) of the reference's padded copy, by index
+        for (int y = warp; y < cp.th; y += kHistWarps) {
+            const uint8_t *row = img + (size_t)reflect101(y0 + y, cp.H) * pitch;
+            for (int x = lane; x < cp.tw; x += 32) atomicAdd(&hist[warp][__ldg(row + reflect101(x0 + x, cp.W))], 1u);
+        }
+    }
+    __syncthreads();
+
+    // one thread per bin from here on
+    int h = 0;
+#pragma unroll
+    for (int w = 0; w < kHistWarps; ++w) h += (int)hist[w][tid];
+
+    if (cp.clip > 0) {
+        int excess = h > cp.clip ? h - cp.clip : 0;
+        if (h > cp.clip) h = cp.clip;
+        int s = __reduce_add_sync(0xffffffffu, excess);
+        if (lane == 0) wsum[warp] = (unsigned)s;
+        __syncthreads();
+        int clipped = 0;
+#pragma unroll
+        for (int w = 0; w < kHistWarps; ++w) clipped += (int)wsum[w];
+        __syncthreads();
+        const int batch = clipped / 256;
+        const int resid = clipped - batch * 256;
+        h += batch;
+        if (resid != 0) {
+            int step = 256 / resid;
+            if (step < 1) step = 1;
+            // for (i = 0; i < 256 && resid > 0; i += step, --resid) hist[i]++
+            if (tid % step == 0 && tid / step < resid) h += 1;
+        }
+    }
+    // inclusive prefix sum over the 256 bins
+    int v = h;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    if (lane == 31) wsum[warp] = (unsigned)v;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < kHistWarps; ++w) base += (w < warp) ? (int)wsum[w] : 0;
+    const int sum = base + v;
+    int q = __float2int_rn((float)sum * cp.lut_scale);
+    q = q < 0 ? 0 : q > 255 ? 255 : q;
+    lut[((size_t)b * (cp.tiles_x * cp.tiles_y) + tile) * 256 + tid] = (uint8_t)q;
+}
+
+struct ApplyBands {
+    int nbands;
+    short y0[96], y1[96], cy[96];
+};
+
+// magic-number conversions: exact for 0..255 and cheaper than I2F/F2I
+__device__ __forceinline__ float u8_to_float(unsigned byte) { return __uint_as_float(0x4B000000u | byte) - 8388608.0f; }
+__device__ __forceinline__ unsigned float_to_u8_rn(float v) {
+    // v in [0, 256): adding 1.5*2^23 rounds to nearest even at integer granularity
+    unsigned r = __float_as_uint(v + 12582912.0f) & 0x1FFu;
+    return r > 255u ? 255u : r;
+}
+
+__global__ void __launch_bounds__(256)
+clahe_apply_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int src_vec4, ClaheParams cp,
+                   ApplyBands bands, const uint8_t *__restrict__ lut, Pyramid pyr, SlotList slots) {
+    extern __shared__ uint32_t comb[];          // [tiles_x + 1][256]: (l11, l12, l21, l22)
+    __shared__ int s_xb[kMaxTiles + 2];
+    const int tid = threadIdx.x;
+    const int band = blockIdx.x, b = blockIdx.y;
+    const int cy = bands.cy[band], y0 = bands.y0[band], y1 = bands.y1[band];
+    const int ncx = cp.tiles_x + 1;
+    const int ty1 = max(cy - 1, 0), ty2 = min(cy, cp.tiles_y - 1);
+    const uint8_t *L = lut + (size_t)b * (cp.tiles_x * cp.tiles_y) * 256;
+    for (int i = tid; i < ncx * 256; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        const int tx1 = max(c - 1, 0), tx2 = min(c, cp.tiles_x - 1);
+        const unsigned l11 = L[(ty1 * cp.tiles_x + tx1) * 256 + v], l12 = L[(ty1 * cp.tiles_x + tx2) * 256 + v];
+        const unsigned l21 = L[(ty2 * cp.tiles_x + tx1) * 256 + v], l22 = L[(ty2 * cp.tiles_x + tx2) * 256 + v];
+        comb[i] = l11 | (l12 << 8) | (l21 << 16) | (l22 << 24);
+    }
+    if (tid < ncx + 1) s_xb[tid] = cp.xb[tid];
+    __syncthreads();
+
+    const uint8_t *img = src[b];
+    uint8_t *dst = pyr.image_origin(0, slots.v[b]);
+    const int dpitch = pyr.lv[0].ipitch;
+    const int groups = (cp.W + 3) >> 2;
+    const int rows = y1 - y0;
+    for (int g = tid; g < groups * rows; g += 256) {
+        const int y = y0 + g / groups;
+        const int x = (g - (g / groups) * groups) << 2;
+        const float tyf = (float)y * cp.inv_th - 0.5f;
+        const float ya = tyf - floorf(tyf), ya1 = 1.0f - ya;
+        const uint8_t *srow = img + (size_t)y * pitch + x;
+        unsigned px;
+        const int nvalid = min(4, cp.W - x);
+        if (src_vec4 && nvalid == 4) {
+            px = __ldg(reinterpret_cast<const unsigned *>(srow));
+        } else {
+            px = 0;
+            for (int i = 0; i < nvalid; ++i) px |= (unsigned)__ldg(srow + i) << (8 * i);
+        }
+        // interpolation cell of the first pixel of the group
+        int c = (x + (cp.tw >> 1)) / cp.tw;
+        c = min(c, ncx - 1);
+        while (c > 0 && x < s_xb[c]) --c;
+        while (c < ncx - 1 && x >= s_xb[c + 1]) ++c;
+        unsigned out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int xi = x + i;
+            while (c < ncx - 1 && xi >= s_xb[c + 1]) ++c;
+            const float txf = (float)xi * cp.inv_tw - 0.5f;
+            const float xa = txf - floorf(txf), xa1 = 1.0f - xa;
+            const unsigned e = comb[(c << 8) + ((px >> (8 * i)) & 255u)];
+            const float l11 = u8_to_float(e & 255u), l12 = u8_to_float((e >> 8) & 255u);
+            const float l21 = u8_to_float((e >> 16) & 255u), l22 = u8_to_float(e >> 24);
+            const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+            out |= float_to_u8_rn(res) << (8 * i);
+        }
+        uint8_t *drow = dst + (size_t)y * dpitch + x;
+        if (nvalid == 4) {
+            *reinterpret_cast<unsigned *>(drow) = out;
+        } else {
+            for (int i = 0; i < nvalid; ++i) drow[i] = (uint8_t)(out >> (8 * i));
+        }
+    }
+}
+
+int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_src, size_t src_pitch,
+                 int src_vec4, const ClaheParams &cp) {
+    const int ntiles = cp.tiles_x * cp.tiles_y;
+    dim3 g1(ntiles, slots.n);
+    clahe_hist_lut_kernel<<<g1, kHistWarps * 32, 0, ctx->stream>>>(d_src, src_pitch, cp, ctx->lut);
+
+    // row bands: split every interpolation cell row into chunks of <= RB rows
+    ApplyBands bands;
+    bands.nbands = 0;
+    int RB = 16;
+    for (;;) {
+        int nb = 0;
+        for (int cy = 0; cy <= cp.tiles_y; ++cy) nb += (cp.yb[cy + 1] - cp.yb[cy] + RB - 1) / RB;
+        if (nb <= 96) break;
+        RB *= 2;
+    }
+    for (int cy = 0; cy <= cp.tiles_y; ++cy)
+        for (int y = cp.yb[cy]; y < cp.yb[cy + 1]; y += RB) {
+            bands.y0[bands.nbands] = (short)y;
+            bands.y1[bands.nbands] = (short)min(y + RB, cp.yb[cy + 1]);
+            bands.cy[bands.nbands] = (short)cy;
+            ++bands.nbands;
+        }
+    dim3 g2(bands.nbands, slots.n);
+    const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t);
+    clahe_apply_kernel<<<g2, 256, smem, ctx->stream>>>(d_src, src_pitch, src_vec4, cp, bands,
+                                                        ctx->lut, ctx->pyr, slots);
+    return 2;
+}
+
+}  // namespace rdfe

@@ -1,0 +1,131 @@
+// fe_internal.cuh -- context layout and kernel launch prototypes shared by the
+// translation units of librdvio_fe.so (sm_100a only; compiled with -fmad=false
+// so every float op is individually rounded like the reference's C++ path).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rdvio_fe.h"
+
+namespace rdfe {
+
+constexpr int kHaloX = 32;          // left halo columns of an image plane (>= win, keeps interior 32-B aligned)
+constexpr int kMaxTiles = 16;       // CLAHE tiles per axis
+constexpr int kSMs = 148;           // B200
+
+// Geometry of one pyramid level.  Image planes carry a materialised
+// REFLECT_101 halo of `win` px (what buildOpticalFlowPyramid keeps around
+// every level); derivative planes carry none -- their zero halo comes from
+// TMA out-of-bounds fill.
+struct LevelGeom {
+    int w, h;
+    int ipitch;          // bytes per padded image row
+    int ph;              // padded rows = h + 2*win
+    size_t islot;        // bytes per slot in the image slab
+    int dpitch;          // bytes per derivative row (w * 4, 64-B aligned)
+    size_t dslot;        // bytes per slot in the derivative slab
+};
+
+// cv::borderInterpolate(p, len, BORDER_REFLECT_101)
+__host__ __device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+struct SlotList {
+    int n;
+    int v[RDFE_MAX_BATCH];
+};
+
+struct Pyramid {
+    int nlevels, win;
+    LevelGeom lv[RDFE_MAX_LEVELS];
+    uint8_t *img[RDFE_MAX_LEVELS];      // slab: [num_slots][ph][ipitch]
+    int16_t *der[RDFE_MAX_LEVELS];      // slab: [num_slots][h][dpitch/2]
+    __host__ __device__ inline uint8_t *image_origin(int l, int slot) const {
+        // pointer to pixel (0,0) of the level interior
+        return img[l] + (size_t)slot * lv[l].islot + (size_t)win * lv[l].ipitch + kHaloX;
+    }
+    __host__ __device__ inline int16_t *deriv_origin(int l, int slot) const {
+        return (int16_t *)((uint8_t *)der[l] + (size_t)slot * lv[l].dslot);
+    }
+};
+
+// CLAHE launch parameters (host-precomputed so float boundary cases are
+// evaluated once, with the same float expressions as the reference).
+struct ClaheParams {
+    int W, H;
+    int tiles_x, tiles_y;
+    int tw, th;              // tile size (of the padded image, if padding applies)
+    int padded;              // W % tiles_x || H % tiles_y  (copyMakeBorder REFLECT_101 quirk)
+    int clip;                // integer clip limit, 0 = no clipping
+    float lut_scale;         // 255.f / (tw*th)
+    float inv_tw, inv_th;
+    // cell boundaries: pixels x in [xb[c], xb[c+1]) interpolate between tile columns c-1 and c
+    int xb[kMaxTiles + 2];
+    int yb[kMaxTiles + 2];
+};
+
+struct DetectScratch {
+    unsigned long long *cand;     // [RDFE_MAX_BATCH][cand_cap] keys: (float bits << 32) | pixel address
+    unsigned *cand_count;         // [RDFE_MAX_BATCH]
+    unsigned *frame_max;          // [RDFE_MAX_BATCH] max response bits (responses <= 0 never win)
+    unsigned *overflow;           // [1]
+    unsigned cand_cap;
+};
+
+}  // namespace rdfe
+
+struct rdfe_ctx {
+    rdfe_config cfg;
+    rdfe::Pyramid pyr;
+    uint8_t *raw;                 // upload staging slab [num_slots][H][raw_pitch]
+    size_t raw_pitch, raw_slot;
+    CUtensorMap tm_img[RDFE_MAX_LEVELS];
+    CUtensorMap tm_der[RDFE_MAX_LEVELS];
+    cudaStream_t stream;
+    bool own_stream;
+    cudaEvent_t ev_t0, ev_t1;
+    // scratch
+    uint8_t *lut;                 // [RDFE_MAX_BATCH][tiles][256]
+    rdfe::DetectScratch det;
+    // host<->device staging for the host-pointer API
+    double *d_xy_a, *d_xy_b;      // [RDFE_MAX_BATCH][max_points][2]
+    int *d_counts;                // [RDFE_MAX_BATCH]
+    char *d_status;               // [RDFE_MAX_BATCH][max_points]
+    float *d_gftt_xy, *d_gftt_resp;
+    int *d_gftt_counts;
+    const uint8_t **d_srcptrs;    // [RDFE_MAX_BATCH] device copy of source pointers
+    uint8_t *slot_used;
+    int64_t launches;
+    int last_clahe_tiles;
+};
+
+namespace rdfe {
+
+void set_error(const char *fmt, ...);
+#define RDFE_CUDA_OK(expr)                                                            \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            rdfe::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                      \
+            return RDFE_ERR_CUDA;                                                     \
+        }                                                                             \
+    } while (0)
+
+// kernel launchers (each returns the number of kernels it launched, or <0 on error)
+int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_src, size_t src_pitch,
+                 int src_vec4, const ClaheParams &cp);
+int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots);
+int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p,
+                             float *d_response /* optional [n][H][W] */);
+int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, double *d_xy, int *d_counts,
+                  int stride, float *d_gftt_xy, float *d_gftt_resp, int *d_gftt_counts);
+int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const rdfe_track_params &p,
+              const double *d_curr_xy, double *d_next_xy, const int *d_counts, int stride, char *d_status);
+
+}  // namespace rdfe

@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path (through the C ABI, librdvio_fe.so) against the CPU oracle
+(oracle/fe_oracle.c, itself pinned against cv2 in test_oracle_*.py) on identical seeded inputs.
+
+Bars (BASELINE.json north_star): preprocessed images, LUTs, pyramids, derivatives, halos and the
+Harris response map bit-exact; selected keypoints identical (set AND order); tracked positions
+within 0.01 px with status agreement >= 99.5 %.
+"""
+import numpy as np
+import pytest
+
+from conftest import random_image
+
+pytestmark = pytest.mark.gpu
+
+TOL_PX = 0.01          # north_star tolerance for tracked positions
+MIN_STATUS_AGREE = 0.995
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import fe_oracle
+    return fe_oracle
+
+
+@pytest.fixture(scope="module")
+def fe752():
+    from rd_vio_b200.frontend import FrontEnd
+    fe = FrontEnd(752, 480, max_level=3, win=21, num_slots=16, max_points=512)
+    yield fe
+    fe.close()
+
+
+def _pre(fe, img, **kw):
+    s = fe.acquire()
+    fe.preprocess([s], [img], **kw)
+    return s
+
+
+@pytest.mark.parametrize("shape,tiles,clip", [
+    ((480, 752), (8, 8), 6.0),      # EuRoC, tiles divide evenly
+    ((478, 750), (8, 8), 6.0),      # both dims padded
+    ((480, 750), (8, 8), 6.0),      # the "divisible dim still gets a full extra tile row" quirk
+    ((477, 752), (8, 8), 6.0),
+    ((135, 241), (8, 8), 6.0),
+    ((200, 300), (4, 6), 2.0),
+    ((720, 1280), (8, 8), 6.0),     # ADVIO-shaped
+])
+def test_clahe_bit_exact(orc, shape, tiles, clip):
+    from rd_vio_b200.frontend import FrontEnd
+    H, W = shape
+    img = random_image(H, W, seed=H * 7 + W)
+    ref, ref_lut = orc.clahe(img, clip, tiles[0], tiles[1], return_lut=True)
+    with FrontEnd(W, H, max_level=1, win=21, num_slots=2, max_points=64) as fe:
+        s = _pre(fe, img, clip_limit=clip, tiles=tiles)
+        lut = fe.download_clahe_lut(0, tiles[0] * tiles[1])
+        got = fe.download_level(s, 0, 0)
+    assert np.array_equal(lut, ref_lut), f"LUT differs in {(lut != ref_lut).sum()} entries"
+    assert np.array_equal(got, ref), f"CLAHE image differs in {(got != ref).sum()} px of {got.size}"
+
+
+@pytest.mark.parametrize("shape,max_level,win", [
+    ((480, 752), 3, 21),
+    ((720, 1280), 4, 21),
+    ((1080, 1920), 5, 31),
+    ((479, 751), 3, 21),           # odd sizes: ceil halving + reflect at odd borders
+    ((100, 130), 3, 21),           # pyramid truncates early (next level <= win)
+])
+def test_pyramid_bit_exact(orc, shape, max_level, win):
+    from rd_vio_b200.frontend import FrontEnd
+    H, W = shape
+    img = random_image(H, W, seed=H + W)
+    with FrontEnd(W, H, max_level=max_level, win=win, num_slots=2, max_points=64) as fe:
+        s = _pre(fe, img)
+        P = orc.Pyramid(orc.clahe(img), win, max_level)
+        assert fe.nlevels == P.nlevels
+        for l in range(P.nlevels):
+            im, dv, halo = fe.download_level(s, l, 0), fe.download_level(s, l, 1), fe.download_level(s, l, 2)
+            assert im.shape == P.level_shape(l)
+            assert np.array_equal(im, P.image(l)), f"level {l} image differs ({(im != P.image(l)).sum()} px)"
+            assert np.array_equal(dv, P.deriv(l)), f"level {l} Scharr differs ({(dv != P.deriv(l)).sum()} values)"
+            want = np.pad(P.image(l), win, mode="reflect")          # numpy 'reflect' == BORDER_REFLECT_101
+            assert np.array_equal(halo, want), f"level {l} halo differs ({(halo != want).sum()} px)"
+
+
+@pytest.mark.parametrize("fma", [0, 1])
+def test_harris_response_bit_exact(orc, fe752, frames0, fma):
+    s = _pre(fe752, frames0[0])
+    try:
+        got = fe752.harris_response(s, harris_fma=fma)
+        ref = orc.harris(orc.clahe(frames0[0]), 0.04, mode=fma)
+        assert np.array_equal(got, ref), f"Harris map differs in {(got != ref).sum()} px, max |d|={np.abs(got - ref).max()}"
+    finally:
+        fe752.release(s)
+
+
+@pytest.mark.parametrize("n_existing,radius,max_points", [(0, 20.0, 150), (47, 20.0, 150), (47, 10.0, 200), (0, 20.0, 1)])
+def test_detect_identical(orc, fe752, frames0, n_existing, radius, max_points):
+    s = _pre(fe752, frames0[1])
+    try:
+        pre = orc.clahe(frames0[1])
+        base, _, _ = orc.detect_keypoints(pre, np.zeros((0, 2)), 150, 20.0)
+        ex = base[::3][:n_existing] + 0.3 if n_existing else np.zeros((0, 2))
+        ref, gxy_ref, gre_ref = orc.detect_keypoints(pre, ex, max_points, radius)
+        got, gxy, gre = fe752.detect([s], [ex], max_points, radius, return_gftt=True)
+        assert np.array_equal(gxy[0], gxy_ref), "GFTT corner list (set or order) differs"
+        assert np.array_equal(gre[0], gre_ref), "GFTT responses differ"
+        assert np.array_equal(got[0], ref), f"keypoints differ: got {len(got[0])}, want {len(ref)}"
+    finally:
+        fe752.release(s)
+
+
+def _track_case(orc, fe, f0, f1, pts, pred, win=21, max_level=3):
+    s0, s1 = _pre(fe, f0), _pre(fe, f1)
+    try:
+        PA, PB = orc.Pyramid(orc.clahe(f0), win, max_level), orc.Pyramid(orc.clahe(f1), win, max_level)
+        ref_xy, ref_st, _ = orc.track_keypoints(PA, PB, pts, pred, win, max_level)
+        got_xy, got_st = fe.track([s0], [s1], [pts], [pred] if pred is not None else None)
+        got_xy, got_st = got_xy[0], got_st[0]
+        agree = (got_st == ref_st).mean()
+        both = (got_st != 0) & (ref_st != 0)
+        err = np.abs(got_xy[both] - ref_xy[both]).max() if both.any() else 0.0
+        return agree, err, int(ref_st.sum()), got_xy, got_st, ref_xy, ref_st
+    finally:
+        fe.release(s0)
+        fe.release(s1)
+
+
+def test_track_parity(orc, fe752, stream0, frames0):
+    pre = orc.clahe(frames0[0])
+    pts, _, _ = orc.detect_keypoints(pre, np.zeros((0, 2)), 150, 20.0)
+    # plus border / outside / sub-pixel cases
+    extra = np.array([[5., 5.], [751., 479.], [-30., 100.], [400., -25.], [760., 300.], [375.5, 240.25],
+                      [20.0, 20.0], [731.9, 459.9], [21.3, 240.7]])
+    pts = np.concatenate([pts, extra], 0)
+    pred = stream0.predict(0, pts)
+    agree, err, nok, *_ = _track_case(orc, fe752, frames0[0], frames0[1], pts, pred)
+    assert nok > 100
+    assert agree >= MIN_STATUS_AGREE, f"status agreement {agree:.4f}"
+    assert err <= TOL_PX, f"max position error {err:.2e} px"
+    # without prediction (next_keypoints empty branch, opencv_image.cpp:81-86)
+    agree, err, nok, *_ = _track_case(orc, fe752, frames0[0], frames0[1], pts, None)
+    assert agree >= MIN_STATUS_AGREE and err <= TOL_PX, (agree, err)
+
+
+def test_track_large_motion_and_failures(orc, fe752, stream0, frames0):
+    """Frames 3 apart with a poor guess: exercises restaging of the search region, the 0.5-px
+    round-trip gate and LK failures."""
+    pre = orc.clahe(frames0[0])
+    pts, _, _ = orc.detect_keypoints(pre, np.zeros((0, 2)), 150, 20.0)
+    rng = np.random.default_rng(5)
+    pred = pts + rng.normal(0, 6.0, pts.shape)
+    agree, err, nok, *_ = _track_case(orc, fe752, frames0[0], frames0[3], pts, pred)
+    assert agree >= MIN_STATUS_AGREE, f"status agreement {agree:.4f} (ok in ref: {nok})"
+    assert err <= TOL_PX, f"max position error {err:.2e} px"
+
+
+def test_batched_equals_single(orc, fe752, stream0, frames0):
+    """n images in one call give exactly what n single calls give (streams share no state)."""
+    n = 4
+    slots = [fe752.acquire() for _ in range(n + 1)]
+    try:
+        fe752.preprocess(slots, frames0[:n + 1])
+        kps = fe752.detect(slots[:n], [np.zeros((0, 2))] * n, 150, 20.0)
+        nxt, st = fe752.track(slots[:n], slots[1:], kps, None)
+        for i in range(n):
+            k1 = fe752.detect([slots[i]], [np.zeros((0, 2))], 150, 20.0)[0]
+            assert np.array_equal(k1, kps[i])
+            n1, s1 = fe752.track([slots[i]], [slots[i + 1]], [kps[i]], None)
+            assert np.array_equal(s1[0], st[i]) and np.array_equal(n1[0], nxt[i])
+            ref = orc.detect_keypoints(orc.clahe(frames0[i]), np.zeros((0, 2)), 150, 20.0)[0]
+            assert np.array_equal(kps[i], ref)
+    finally:
+        for s in slots:
+            fe752.release(s)
+
+
+def test_large_window_config(orc):
+    """Config 4 shape: 1920x1080, maxLevel 5, 31x31 window (GPU-only setting; oracle = same restatement)."""
+    from rd_vio_b200.frontend import FrontEnd
+    from rd_vio_b200.synthetic import SyntheticStream
+    st = SyntheticStream(3, 1920, 1080)
+    f0, f1 = st.frame(0), st.frame(1)
+    with FrontEnd(1920, 1080, max_level=5, win=31, num_slots=2, max_points=1200) as fe:
+        pre = orc.clahe(f0)
+        pts, _, _ = orc.detect_keypoints(pre, np.zeros((0, 2)), 1000, 20.0)
+        got = fe_detect = None
+        s0, s1 = _pre(fe, f0), _pre(fe, f1)
+        got = fe.detect([s0], [np.zeros((0, 2))], 1000, 20.0)[0]
+        assert np.array_equal(got, pts), f"detect differs: {len(got)} vs {len(pts)}"
+        pred = st.predict(0, pts)
+        PA, PB = orc.Pyramid(pre, 31, 5), orc.Pyramid(orc.clahe(f1), 31, 5)
+        ref_xy, ref_st, _ = orc.track_keypoints(PA, PB, pts, pred, 31, 5)
+        got_xy, got_st = fe.track([s0], [s1], [pts], [pred])
+        agree = (got_st[0] == ref_st).mean()
+        both = (got_st[0] != 0) & (ref_st != 0)
+        err = np.abs(got_xy[0][both] - ref_xy[both]).max()
+        assert agree >= MIN_STATUS_AGREE and err <= TOL_PX, (agree, err)
