@@ -43,8 +43,9 @@ static int make_tensor_maps(rdfe_ctx *ctx) {
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return RDFE_ERR_CUDA; }
     const Pyramid &pyr = ctx->pyr;
     const int win = pyr.win;
-    const cuuint32_t jw = win == 21 ? 32 : 48, jh = jw;
-    const cuuint32_t dw = win == 21 ? 24 : 32, dh = win == 21 ? 22 : 32;
+    // box sizes must match LKCfg<win> in lk.cu (inner extents padded so the box can start 16-B aligned)
+    const cuuint32_t jw = win == 21 ? 48 : 64, jh = win == 21 ? 32 : 48;
+    const cuuint32_t dw = win == 21 ? 28 : 36, dh = win == 21 ? 22 : 32;
     for (int l = 0; l < pyr.nlevels; ++l) {
         const LevelGeom &g = pyr.lv[l];
         {

@@ -12,6 +12,9 @@
 //     coordinates {x, y, slot}) completing on a per-warp mbarrier: the (win+1)^2 template patch
 //     of I, its Scharr derivative patch (uint32 = int16 pair; the zero halo of the reference's
 //     derivative buffers is TMA out-of-bounds fill) and a J search region (window + margin);
+//     TMA needs the innermost box coordinate 16-byte aligned (measured on B200: an unaligned
+//     start raises "illegal instruction"), so boxes start at the aligned-down column and are
+//     15 bytes (3 derivative elements) wider; the residual offset is applied in shared memory;
 //   * a lane owns (row, 7- or 8-pixel segment) items of the window; the template lives in
 //     registers for the whole level; the J bytes a lane needs are fetched from shared memory as
 //     aligned 32-bit words only when the window's INTEGER origin moves, and re-paired with
@@ -19,17 +22,18 @@
 //   * sums (A11,A12,A22,b1,b2) are accumulated as exact integers per lane and reduced with
 //     REDUX; one int64->float conversion.  (OpenCV accumulates in float32; the exact sum is the
 //     value that accumulation approximates -- measured deviation < 1e-3 px.)
+#include <cstdio>
 #include "fe_internal.cuh"
 
 namespace rdfe {
 
 template <int WIN> struct LKCfg;
 template <> struct LKCfg<21> {
-    static constexpr int SEG = 7, NSEG = 3, JW = 32, JH = 32, DW = 24, DH = 22, MARGIN = 5, WARPS = 8;
+    static constexpr int SEG = 7, NSEG = 3, JW = 48, JH = 32, DW = 28, DH = 22, MARGIN = 5, WARPS = 8;
     static constexpr bool PACKED = false;
 };
 template <> struct LKCfg<31> {
-    static constexpr int SEG = 8, NSEG = 4, JW = 48, JH = 48, DW = 32, DH = 32, MARGIN = 8, WARPS = 4;
+    static constexpr int SEG = 8, NSEG = 4, JW = 64, JH = 48, DW = 36, DH = 32, MARGIN = 8, WARPS = 4;
     static constexpr bool PACKED = true;
 };
 
@@ -77,7 +81,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // Bounded wait: a TMA that never completes (bad descriptor) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 22)) __trap();
+        if (spins > (1u << 20)) {
+            if ((threadIdx.x & 31) == 0) printf("rdfe lk: TMA wait timed out (block %d,%d warp %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5, parity);
+            __trap();
+        }
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar) {
     asm volatile(
@@ -178,14 +185,20 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
             if (level == 0) status = 0;
             continue;
         }
-        // ---- stage I patch, dI patch and the J search region
-        float jnx = nx - half, jny = ny - half;
-        int jx0 = (int)floorf(jnx) - C::MARGIN, jy0 = (int)floorf(jny) - C::MARGIN;
+        // ---- stage I patch, dI patch and the J search region (16-B aligned box starts)
+        const int ixg = ipx + kHaloX, ixa = ixg & ~15, ioff = ixg - ixa;
+        const int dxa = ipx & ~3, doff = ipx - dxa;
+        int jx0, jy0;                                    // interior coordinates of the staged J region origin
+        {
+            const int jxg = ((int)floorf(nx - half) - C::MARGIN) + kHaloX;
+            jx0 = (jxg & ~15) - kHaloX;
+            jy0 = (int)floorf(ny - half) - C::MARGIN;
+        }
         __syncwarp();
         if (lane == 0) {
             mbar_expect_tx(&ws.bar, 2u * JW * JH + 4u * DW * C::DH);
-            tma_load_3d(ws.ipatch, &maps.img[level], ipx + kHaloX, ipy + win_rt, slotA, &ws.bar);
-            tma_load_3d(ws.dpatch, &maps.der[level], ipx, ipy, slotA, &ws.bar);
+            tma_load_3d(ws.ipatch, &maps.img[level], ixa, ipy + win_rt, slotA, &ws.bar);
+            tma_load_3d(ws.dpatch, &maps.der[level], dxa, ipy, slotA, &ws.bar);
             tma_load_3d(ws.jreg, &maps.img[level], jx0 + kHaloX, jy0 + win_rt, slotB, &ws.bar);
         }
         mbar_wait(&ws.bar, phase);
@@ -202,14 +215,14 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
             const unsigned wt = (unsigned)iw00 | ((unsigned)iw01 << 16), wb = (unsigned)iw10 | ((unsigned)iw11 << 16);
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) {
-                const int o = irow[r] * JW + iseg[r] * SEG;
+                const int o = irow[r] * JW + ioff + iseg[r] * SEG;
                 const Pairs t = load_pairs(ws.ipatch, o), b = load_pairs(ws.ipatch, o + JW);
                 int iv[8];
                 iv[0] = sample<0>(t, b, wt, wb); iv[1] = sample<1>(t, b, wt, wb);
                 iv[2] = sample<2>(t, b, wt, wb); iv[3] = sample<3>(t, b, wt, wb);
                 iv[4] = sample<4>(t, b, wt, wb); iv[5] = sample<5>(t, b, wt, wb);
                 iv[6] = sample<6>(t, b, wt, wb); iv[7] = sample<7>(t, b, wt, wb);
-                const uint32_t *d0 = ws.dpatch + irow[r] * DW + iseg[r] * SEG;
+                const uint32_t *d0 = ws.dpatch + irow[r] * DW + doff + iseg[r] * SEG;
                 const uint32_t *d1 = d0 + DW;
                 uint32_t dt = d0[0], db = d1[0];
 #pragma unroll
@@ -254,7 +267,8 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
             if (inx != cinx || iny != ciny) {
                 if (inx < jx0 || inx > jx0 + (JW - (WIN + 1)) || iny < jy0 || iny > jy0 + (JH - (WIN + 1))) {
                     // the window left the staged region: restage around the current position
-                    jx0 = inx - C::MARGIN; jy0 = iny - C::MARGIN;
+                    jx0 = (((inx - C::MARGIN) + kHaloX) & ~15) - kHaloX;
+                    jy0 = iny - C::MARGIN;
                     __syncwarp();
                     if (lane == 0) {
                         mbar_expect_tx(&ws.bar, (uint32_t)(JW * JH));
