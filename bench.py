@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the rd_vio visual front-end step (BASELINE.json metric).
+
+One step = one new frame for every camera stream of the batch:
+    preprocess(new) + track_keypoints(prev -> new, forward+backward LK + gating) + detect_keypoints(new)
+i.e. FeatureTracker::run's per-frame plugin calls (/root/reference/src/rdvio/src/feature_tracker.cpp:32-98).
+
+Workload at N GPUs: BASELINE.json configs[1] per GPU -- 752x480, 64 independent streams, 150 carried
+keypoints + 150 detect, maxLevel 3 (4 images), 21x21 window; streams are partitioned across ranks
+(weak scaling, no data-path collective: streams share no state).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun by the driver)
+  python bench.py --impl reference ...                   the reference's OpenCV path on host cores
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`: same metric through the host-pointer C ABI (H2D of every frame + D2H of results in the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rd_vio_b200 import workload as WL  # noqa: E402
+
+METRIC = "frames/s detect+KLT-track @752x480"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="euroc", choices=list(WL.WORKLOADS))
+    ap.add_argument("--streams", type=int, default=64, help="streams per GPU")
+    ap.add_argument("--ring", type=int, default=8, help="distinct frames per stream kept resident")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=20, help="extra steps with per-kernel events")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def run_cpu(args, wl, stream_ids, steps, warmup, budget_s=None):
+    """Times the reference's CPU path (oracle/) on all host cores. Returns dict."""
+    from oracle.cpu_frontend import CpuFrontEndPool, pick_backend
+    backend = pick_backend()
+    cores = os.cpu_count() or 1
+    pool = CpuFrontEndPool(stream_ids, wl, args.ring, backend, workers=cores)
+    try:
+        for t in range(warmup):
+            pool.step(t)
+        times, t = [], warmup
+        t_begin = time.perf_counter()
+        for _ in range(steps):
+            times.append(pool.step(t)); t += 1
+            if budget_s and time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+                break
+        total = float(np.sum(times))
+        return {"value": len(stream_ids) * len(times) / total, "unit": UNIT, "cores": pool.workers,
+                "kind": "reference" if backend == "cv2" else "port",
+                "sample": f"{len(times)} steps x {len(stream_ids)} streams = {len(times) * len(stream_ids)} frames of the same "
+                          f"synthetic workload, {pool.workers} worker processes x 1 OpenCV thread "
+                          f"({'cv2 ' + __import__('cv2').__version__ if backend == 'cv2' else 'C oracle port'})",
+                "ms_per_step": 1e3 * total / len(times), "steps": len(times)}
+    finally:
+        pool.close()
+
+
+def main_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    stream_ids = list(range(args.streams))
+    WL.ensure_rings(stream_ids, wl["width"], wl["height"], args.ring)
+    res = run_cpu(args, wl, stream_ids, args.steps, max(args.warmup, 1), budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": res["steps"], "warmup": max(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
+        "config": workload_config(args, wl, 1),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, wl, n_gpus):
+    return {"workload": f"BASELINE configs[1]: {wl['width']}x{wl['height']} u8, {args.streams} independent streams per GPU "
+                        f"batched per launch, {wl['points']} carried keypoints + {wl['points']}-point detect, maxLevel "
+                        f"{wl['max_level']} ({wl['max_level'] + 1} images), {wl['win']}x{wl['win']} LK window, CLAHE 6.0/8x8, "
+                        f"Harris-GFTT q=1e-3 minDist 20, Poisson radius 20, LK (30, 0.01)",
+            "streams_per_gpu": args.streams, "global_streams": args.streams * n_gpus, "ring_frames": args.ring,
+            "parallelism": f"streams partitioned across {n_gpus} GPU(s), no collective",
+            "l2": f"inputs larger than L2: {args.streams}x{args.ring} resident frames = "
+                  f"{args.streams * args.ring * wl['width'] * wl['height'] / 1e6:.0f} MB cycled (L2 126 MB)"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main_b200(args, wl):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    stream_ids = [rank * args.streams + i for i in range(args.streams)]
+    # frame rings: generated once per box, before CUDA is touched
+    WL.ensure_rings(stream_ids, wl["width"], wl["height"], args.ring,
+                    workers=max(1, (os.cpu_count() or 1) // max(world, 1)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from rd_vio_b200 import _native as N
+    from rd_vio_b200.frontend import FrontEnd
+    from rd_vio_b200.synthetic import SyntheticStream
+    L = N.lib()
+    W, H, NP, T, S = wl["width"], wl["height"], wl["points"], args.ring, args.streams
+    stride = 2 * NP
+    tstream = torch.cuda.current_stream()
+    fe = FrontEnd(W, H, wl["max_level"], wl["win"], num_slots=2 * S, max_points=max(stride, 512), device=local,
+                  stream=tstream.cuda_stream)
+    h = fe.handle
+    slotsA = np.array([fe.acquire() for _ in range(S)], np.int32)
+    slotsB = np.array([fe.acquire() for _ in range(S)], np.int32)
+    slots = [slotsA, slotsB]
+
+    # ---- resident inputs: frames [S][T][H][W] in HBM (and pinned on the host for e2e)
+    host_frames = torch.empty((S, T, H, W), dtype=torch.uint8, pin_memory=True)
+    hf = host_frames.numpy()
+    for i, sid in enumerate(stream_ids):
+        hf[i] = WL.load_ring(sid, W, H, T)
+    dev_frames = host_frames.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    def frame_ptrs(base_ptr, k):
+        return (C.c_void_p * S)(*[base_ptr + ((i * T + k) * H * W) for i in range(S)])
+
+    dptrs = [frame_ptrs(dev_frames.data_ptr(), k) for k in range(T)]
+    hptrs = [frame_ptrs(host_frames.data_ptr(), k) for k in range(T)]
+
+    dp = fe.detect_params(max_points=NP, keypoint_distance=20.0)
+    tp = fe.track_params(has_prediction=1)
+
+    def vp(t):
+        return C.c_void_p(t.data_ptr())
+
+    # ---- carried keypoints of every ring frame (our own detect, untimed) + IMU-style predictions
+    curr_xy = torch.zeros((T, S, stride, 2), dtype=torch.float64, device="cuda")
+    cnt = torch.zeros((T, S), dtype=torch.int32, device="cuda")
+    for k in range(T):
+        N.check(L.rdfe_preprocess_batch_dev(h, slotsA.ctypes.data, S, dptrs[k], W, 6.0, 8, 8), "preprocess")
+        N.check(L.rdfe_detect_batch_dev(h, slotsA.ctypes.data, S, C.byref(dp), vp(curr_xy[k]), vp(cnt[k]), stride,
+                                        None, None, None), "detect")
+    fe.sync()
+    curr_h, cnt_h = curr_xy.cpu().numpy(), cnt.cpu().numpy()
+    pred_h = np.zeros_like(curr_h)
+    for i, sid in enumerate(stream_ids):
+        st = SyntheticStream(sid, W, H, period=T)
+        for k in range(T):
+            n = cnt_h[k, i]
+            pred_h[k, i, :n] = st.predict(k, curr_h[k, i, :n])
+    pred_xy = torch.from_numpy(pred_h).cuda()
+    work_xy = torch.zeros((S, stride, 2), dtype=torch.float64, device="cuda")
+    work_cnt = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    status = torch.zeros((S, stride), dtype=torch.int8, device="cuda")
+    mean_pts = float(cnt_h.mean())
+
+    def step_dev(t):
+        k = t % T
+        prev, new = slots[t % 2], slots[(t + 1) % 2]
+        N.check(L.rdfe_preprocess_batch_dev(h, new.ctypes.data, S, dptrs[(k + 1) % T], W, 6.0, 8, 8), "preprocess")
+        work_xy.copy_(pred_xy[k], non_blocking=True)
+        work_cnt.copy_(cnt[k], non_blocking=True)
+        N.check(L.rdfe_track_batch_dev(h, prev.ctypes.data, new.ctypes.data, S, C.byref(tp), vp(curr_xy[k]), vp(work_xy),
+                                       vp(cnt[k]), stride, vp(status)), "track")
+        N.check(L.rdfe_detect_batch_dev(h, new.ctypes.data, S, C.byref(dp), vp(work_xy), vp(work_cnt), stride,
+                                        None, None, None), "detect")
+
+    # prime: frame 0 preprocessed into the "prev" slots of step 0
+    N.check(L.rdfe_preprocess_batch_dev(h, slots[0].ctypes.data, S, dptrs[0], W, 6.0, 8, 8), "preprocess")
+    fe.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 0
+    for _ in range(max(args.warmup, 3)):
+        step_dev(t); t += 1
+    # keep the step parity so prev/new slots stay consistent: warm-up count may be odd, that is fine (t carries on)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = fe.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev(t); t += 1
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = fe.kernel_launches() - launches0
+    tracked_ok = float(status[:, :NP].float().mean().item())
+    fe.sync()   # also surfaces a candidate-buffer overflow
+    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    value = world * S * args.steps / (ms_max * 1e-3)
+
+    # ---- per-kernel device time (separate pass, events around every launch) -> roofline of the dominant kernel
+    prof = None
+    if rank == 0 and args.profile_steps > 0:
+        N.check(L.rdfe_profile_enable(h, 1), "profile_enable")
+        for _ in range(args.profile_steps):
+            step_dev(t); t += 1
+        nk = L.rdfe_profile_num_kernels()
+        pms = (C.c_double * nk)(); pn = (C.c_int64 * nk)()
+        N.check(L.rdfe_profile_collect(h, pms, pn), "profile_collect")
+        N.check(L.rdfe_profile_enable(h, 0), "profile_enable")
+        prof = {L.rdfe_profile_kernel_name(i).decode(): {"ms_per_step": pms[i] / args.profile_steps,
+                                                        "launches_per_step": pn[i] / args.profile_steps,
+                                                        "us_per_launch": 1e3 * pms[i] / max(pn[i], 1)} for i in range(nk)}
+    elif args.profile_steps > 0:
+        for _ in range(args.profile_steps):
+            step_dev(t); t += 1
+        fe.sync()
+
+    # ---- end to end through the host-pointer C ABI: pinned host frames + keypoints in, results out, every step
+    e2e = None
+    if not args.no_e2e:
+        h_curr = torch.from_numpy(curr_h).pin_memory().numpy()
+        h_pred = torch.from_numpy(pred_h).pin_memory().numpy()
+        h_cnt = cnt_h.copy()
+        h_next = torch.empty((S, stride, 2), dtype=torch.float64).pin_memory().numpy()
+        h_status = torch.empty((S, stride), dtype=torch.int8).pin_memory().numpy()
+        h_wcnt = np.zeros(S, np.int32)
+
+        def step_host(tt):
+            k = tt % T
+            prev, new = slots[tt % 2], slots[(tt + 1) % 2]
+            N.check(L.rdfe_preprocess_batch(h, new.ctypes.data, S, hptrs[(k + 1) % T], W, 6.0, 8, 8), "preprocess")
+            h_next[:] = h_pred[k]
+            N.check(L.rdfe_track_batch(h, prev.ctypes.data, new.ctypes.data, S, C.byref(tp), h_curr[k].ctypes.data,
+                                       h_next.ctypes.data, h_cnt[k].ctypes.data, stride, h_status.ctypes.data), "track")
+            h_wcnt[:] = h_cnt[k]
+            N.check(L.rdfe_detect_batch(h, new.ctypes.data, S, C.byref(dp), h_next.ctypes.data, h_wcnt.ctypes.data, stride,
+                                        None, None, None), "detect")
+
+        h2d = S * H * W + 2 * S * stride * 16 + S * 4 + S * stride * 16 + S * 4
+        d2h = S * stride * 16 + S * stride + S * stride * 16 + S * 4
+        e_steps = max(10, min(args.steps, 100))
+        for _ in range(3):
+            step_host(t); t += 1
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(e_steps):
+            step_host(t); t += 1
+        barrier()
+        sec = time.perf_counter() - w0
+        sec_t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(sec_t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * S * e_steps / float(sec_t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "steps": e_steps,
+               "how": "rdfe_preprocess_batch + rdfe_track_batch + rdfe_detect_batch with pinned HOST buffers; every "
+                      "step copies its frames and keypoints H2D and its tracked/detected keypoints + status D2H; wall "
+                      "clock bracketed by barrier+synchronize, max over ranks"}
+
+    if rank != 0:
+        fe.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel
+    hbm_peak, peak_src = peaks()
+    total_bytes, stage_bytes = WL.algorithmic_bytes(W, H, NP, wl["max_level"], wl["win"])
+    roofline = None
+    if prof:
+        dom = max(prof, key=lambda kname: prof[kname]["ms_per_step"])
+        per_launch_bytes = stage_bytes.get(dom, 0) * S / max(prof[dom]["launches_per_step"], 1)
+        ach = per_launch_bytes / (prof[dom]["us_per_launch"] * 1e-6) / 1e9 if prof[dom]["us_per_launch"] > 0 else 0.0
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": per_launch_bytes, "us_per_launch": prof[dom]["us_per_launch"],
+                    "share_of_step": prof[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in prof.values()), 1e-12)}
+    step_frac = (value / world) * total_bytes / 1e9 / hbm_peak
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cpu_streams = stream_ids[:min(S, 64)]
+            r = run_cpu(args, wl, cpu_streams, steps=40, warmup=1, budget_s=20.0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:   # report, never hide
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
+        "config": workload_config(args, wl, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "hbm_roofline_step": {"algorithmic_bytes_per_frame": total_bytes, "frac_per_gpu": step_frac,
+                              "peak_gbs": hbm_peak, "peak_source": peak_src},
+        "kernels": prof, "mean_carried_keypoints": mean_pts, "tracked_ok_frac": tracked_ok,
+    }
+    print(json.dumps(line), flush=True)
+    fe.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    wl = WL.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return main_reference(args, wl)
+    return main_b200(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,6 +167,14 @@ RDFE_API int rdfe_timer_start(rdfe_ctx *ctx);
 RDFE_API int rdfe_timer_stop(rdfe_ctx *ctx);
 RDFE_API int rdfe_timer_elapsed_ms(rdfe_ctx *ctx, float *ms);
 
+/* Per-kernel CUDA-event timing (off by default).  While enabled every kernel launch is
+ * bracketed by two events on the context's stream; collect() synchronises and returns the
+ * accumulated device milliseconds and launch counts per kernel id since enable(). */
+RDFE_API int rdfe_profile_num_kernels(void);
+RDFE_API const char *rdfe_profile_kernel_name(int id);
+RDFE_API int rdfe_profile_enable(rdfe_ctx *ctx, int on);
+RDFE_API int rdfe_profile_collect(rdfe_ctx *ctx, double *ms, int64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

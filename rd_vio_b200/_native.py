@@ -63,6 +63,10 @@ SYMBOLS = {
     "rdfe_host_free": (_i, [_vp, _vp]),
     "rdfe_memcpy_h2d": (_i, [_vp, _vp, _vp, _sz, _i]),
     "rdfe_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "rdfe_profile_num_kernels": (_i, []),
+    "rdfe_profile_kernel_name": (C.c_char_p, [_i]),
+    "rdfe_profile_enable": (_i, [_vp, _i]),
+    "rdfe_profile_collect": (_i, [_vp, _vp, _vp]),
     "rdfe_timer_start": (_i, [_vp]),
     "rdfe_timer_stop": (_i, [_vp]),
     "rdfe_timer_elapsed_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -256,6 +256,8 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     CK(cudaEventCreate(&ctx->ev_t0));
     CK(cudaEventCreate(&ctx->ev_t1));
+    ctx->prof_ev = (cudaEvent_t *)calloc(2 * kProfMax, sizeof(cudaEvent_t));
+    for (int i = 0; i < 2 * kProfMax; ++i) CK(cudaEventCreate(&ctx->prof_ev[i]));
 #undef CK
     ctx->slot_used = (uint8_t *)calloc((size_t)cfg->num_slots, 1);
     int rc = make_tensor_maps(ctx);
@@ -273,6 +275,10 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     cudaFree(ctx->det.cand); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.overflow);
     cudaFree(ctx->d_xy_a); cudaFree(ctx->d_xy_b); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->d_gftt_xy); cudaFree(ctx->d_gftt_resp); cudaFree(ctx->d_gftt_counts); cudaFree(ctx->d_srcptrs);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < 2 * kProfMax; ++i) if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
+        free(ctx->prof_ev);
+    }
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -560,6 +566,35 @@ int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t b
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
     RDFE_CUDA_OK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (!async) RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return RDFE_OK;
+}
+
+static const char *const kKernelNames[K_COUNT] = {"clahe_hist_lut", "clahe_apply", "pyrdown", "scharr", "halo",
+                                                  "harris_nms", "select", "lk_track"};
+
+int rdfe_profile_num_kernels(void) { return K_COUNT; }
+const char *rdfe_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }
+
+int rdfe_profile_enable(rdfe_ctx *ctx, int on) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->prof_on = on != 0;
+    ctx->prof_used = 0;
+    for (int k = 0; k < K_COUNT; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
+    return RDFE_OK;
+}
+
+int rdfe_profile_collect(rdfe_ctx *ctx, double *ms, int64_t *launches) {
+    if (!ctx || !ms || !launches) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->prof_used; ++i) {
+        float t = 0.f;
+        RDFE_CUDA_OK(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ctx->prof_ms[ctx->prof_kid[i]] += t;
+        ctx->prof_n[ctx->prof_kid[i]] += 1;
+    }
+    ctx->prof_used = 0;
+    for (int k = 0; k < K_COUNT; ++k) { ms[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_n[k]; }
     return RDFE_OK;
 }
 

@@ -69,6 +69,11 @@ struct ClaheParams {
     int yb[kMaxTiles + 2];
 };
 
+enum KernelId {
+    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HALO, K_HARRIS, K_SELECT, K_LK, K_COUNT
+};
+constexpr int kProfMax = 4096;      // timed launches between two rdfe_profile_collect calls
+
 struct DetectScratch {
     unsigned long long *cand;     // [RDFE_MAX_BATCH][cand_cap] keys: (float bits << 32) | pixel address
     unsigned *cand_count;         // [RDFE_MAX_BATCH]
@@ -102,6 +107,13 @@ struct rdfe_ctx {
     uint8_t *slot_used;
     int64_t launches;
     int last_clahe_tiles;
+    // optional per-kernel CUDA-event timing (rdfe_profile_*)
+    bool prof_on;
+    int prof_used;
+    cudaEvent_t *prof_ev;         // [2 * kProfMax]
+    int prof_kid[rdfe::kProfMax];
+    double prof_ms[rdfe::K_COUNT];
+    int64_t prof_n[rdfe::K_COUNT];
 };
 
 namespace rdfe {
@@ -115,6 +127,24 @@ void set_error(const char *fmt, ...);
                             __FILE__, __LINE__);                                      \
             return RDFE_ERR_CUDA;                                                     \
         }                                                                             \
+    } while (0)
+
+// Bracket one kernel launch with CUDA events when profiling is on.
+inline int prof_begin(rdfe_ctx *ctx, int kid) {
+    if (!ctx->prof_on || ctx->prof_used >= kProfMax) return -1;
+    const int i = ctx->prof_used++;
+    ctx->prof_kid[i] = kid;
+    cudaEventRecord(ctx->prof_ev[2 * i], ctx->stream);
+    return i;
+}
+inline void prof_end(rdfe_ctx *ctx, int i) {
+    if (i >= 0) cudaEventRecord(ctx->prof_ev[2 * i + 1], ctx->stream);
+}
+#define RDFE_LAUNCH(ctx, KID, ...)                     \
+    do {                                               \
+        const int pi__ = rdfe::prof_begin(ctx, KID);   \
+        __VA_ARGS__;                                   \
+        rdfe::prof_end(ctx, pi__);                     \
     } while (0)
 
 // kernel launchers (each returns the number of kernels it launched, or <0 on error)

@@ -171,9 +171,9 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
     detect_reset_kernel<<<1, RDFE_MAX_BATCH, 0, ctx->stream>>>(ctx->det, slots.n);
     dim3 grid((g.w + HT_W - 1) / HT_W, (g.h + HT_H - 1) / HT_H, slots.n);
     if (p.harris_fma)
-        harris_nms_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response);
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response)));
     else
-        harris_nms_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response);
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response)));
     return 2;
 }
 

@@ -395,12 +395,12 @@ int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const r
     P.stride = stride;
     if (pyr.win == 21) {
         dim3 grid((stride + LKCfg<21>::WARPS - 1) / LKCfg<21>::WARPS, curr.n);
-        lk_track_kernel<21><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->stream>>>(maps, P, curr, next, d_curr_xy, d_next_xy,
-                                                                              d_counts, d_status);
+        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->stream>>>(maps, P, curr, next, d_curr_xy,
+                                                                                                      d_next_xy, d_counts, d_status)));
     } else if (pyr.win == 31) {
         dim3 grid((stride + LKCfg<31>::WARPS - 1) / LKCfg<31>::WARPS, curr.n);
-        lk_track_kernel<31><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->stream>>>(maps, P, curr, next, d_curr_xy, d_next_xy,
-                                                                              d_counts, d_status);
+        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->stream>>>(maps, P, curr, next, d_curr_xy,
+                                                                                                      d_next_xy, d_counts, d_status)));
     } else {
         set_error("LK window %d unsupported (21 or 31)", pyr.win);
         return RDFE_ERR_UNSUPPORTED;

@@ -127,7 +127,7 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
     for (int l = 0; l + 1 < pyr.nlevels; ++l) {
         const LevelGeom &gd = pyr.lv[l + 1];
         dim3 grid((gd.w + PD_TW - 1) / PD_TW, (gd.h + PD_TH - 1) / PD_TH, slots.n);
-        pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(pyr, slots, l);
+        RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(pyr, slots, l)));
         ++launches;
     }
     TileTable tt;
@@ -144,8 +144,8 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
     }
     tt.first[pyr.nlevels] = nt;
     ht.first[pyr.nlevels] = nh;
-    scharr_kernel<<<dim3(nt, slots.n), 256, 0, ctx->stream>>>(pyr, slots, tt);
-    halo_kernel<<<dim3(nh, slots.n), 256, 0, ctx->stream>>>(pyr, slots, ht);
+    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3(nt, slots.n), 256, 0, ctx->stream>>>(pyr, slots, tt)));
+    RDFE_LAUNCH(ctx, K_HALO, (halo_kernel<<<dim3(nh, slots.n), 256, 0, ctx->stream>>>(pyr, slots, ht)));
     return launches + 2;
 }
 

@@ -328,8 +328,8 @@ int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params
         }
         s_attr = smem;
     }
-    select_kernel<<<slots.n, SEL_THREADS, smem, ctx->stream>>>(ctx->det, sp, slots, d_xy, d_counts, d_gftt_xy, d_gftt_resp,
-                                                               d_gftt_counts);
+    RDFE_LAUNCH(ctx, K_SELECT, (select_kernel<<<slots.n, SEL_THREADS, smem, ctx->stream>>>(ctx->det, sp, slots, d_xy, d_counts, d_gftt_xy,
+                                                                                            d_gftt_resp, d_gftt_counts)));
     return 1;
 }
 

@@ -51,8 +51,8 @@ class SyntheticStream:
         s = width / 752.0
         self.fx, self.fy, self.cx, self.cy = (_EUROC_K[0] * s, _EUROC_K[1] * s,
                                               _EUROC_K[2] * s, _EUROC_K[3] * height / 480.0)
-        rng = np.random.default_rng(stream_id * 1000 + 7)
-        self._tex = [_texture(rng, self.TEX_SIZE) for _ in self.PLANES]
+        self._stream_id = stream_id
+        self._tex_cache = None           # textures are built lazily: flow()/predict() never need them
         self._noise_seed = stream_id * 1000 + 7
         trng = np.random.default_rng(traj_seed + 31 * stream_id)
         # smooth periodic trajectory: <=1.5 deg/frame rotation, <=~4 px/frame flow at 4 m
@@ -61,6 +61,13 @@ class SyntheticStream:
         self._amp_r = trng.uniform(0.5, 1.0, 3) * np.deg2rad([0.5, 0.5, 1.0]) * self.period / (2 * np.pi)
         ys, xs = np.mgrid[0:self.H, 0:self.W]
         self._rays = np.stack([(xs - self.cx) / self.fx, (ys - self.cy) / self.fy, np.ones_like(xs, float)], -1)
+
+    @property
+    def _tex(self):
+        if self._tex_cache is None:
+            rng = np.random.default_rng(self._stream_id * 1000 + 7)
+            self._tex_cache = [_texture(rng, self.TEX_SIZE) for _ in self.PLANES]
+        return self._tex_cache
 
     # -- camera model
     def pose(self, k):
