@@ -185,7 +185,10 @@ def main_b200(args, wl):
     L = N.lib()
     W, H, NP, T, S = wl["width"], wl["height"], wl["points"], args.ring, args.streams
     stride = 2 * NP
-    tstream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch (copies, events) and the library (kernels): the legacy
+    # default stream has handle 0, which the C ABI reads as "create your own"
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
     fe = FrontEnd(W, H, wl["max_level"], wl["win"], num_slots=2 * S, max_points=max(stride, 512), device=local,
                   stream=tstream.cuda_stream)
     h = fe.handle

@@ -1,0 +1,55 @@
+"""CPU: the oracle against LIVE cv2 (the reference's own OpenCV calls) on seeded inputs, when cv2 is importable."""
+import numpy as np
+import pytest
+
+from conftest import random_image
+from oracle import fe_oracle as orc
+from oracle.cv2_reference import HAVE_CV2, Cv2Image
+
+pytestmark = pytest.mark.skipif(not HAVE_CV2, reason="cv2 not importable")
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (478, 750), (480, 750), (477, 752), (135, 241), (720, 1280)])
+def test_clahe_vs_cv2(shape):
+    import cv2
+    img = random_image(*shape, seed=shape[0])
+    assert np.array_equal(cv2.createCLAHE(6.0, (8, 8)).apply(img), orc.clahe(img))
+
+
+@pytest.mark.parametrize("shape,max_level,win", [((480, 752), 3, 21), ((479, 751), 3, 21), ((100, 130), 3, 21), ((540, 960), 4, 31)])
+def test_pyramid_vs_cv2(shape, max_level, win):
+    import cv2
+    img = random_image(*shape, seed=7)
+    n, pyr = cv2.buildOpticalFlowPyramid(img, (win, win), max_level, None, True)
+    P = orc.Pyramid(img, win, max_level)
+    assert P.nlevels == n + 1
+    for l in range(P.nlevels):
+        assert np.array_equal(pyr[2 * l], P.image(l)) and np.array_equal(pyr[2 * l + 1], P.deriv(l))
+
+
+def test_harris_and_detect_vs_cv2(frames0):
+    import cv2
+    cv2.setUseOptimized(False)
+    try:
+        A = Cv2Image(frames0[0])
+        A.preprocess()
+        assert np.array_equal(cv2.cornerHarris(A.image, 3, 3, 0.04), orc.harris(A.image))
+        for ex, r, k in ((np.zeros((0, 2)), 20.0, 150), (np.array([[100.2, 100.7], [400.0, 300.0]]), 10.0, 200)):
+            assert np.array_equal(A.detect_keypoints(ex, k, r), orc.detect_keypoints(A.image, ex, k, r)[0])
+    finally:
+        cv2.setUseOptimized(True)
+
+
+def test_track_vs_cv2(stream0, frames0):
+    A, B = Cv2Image(frames0[0]), Cv2Image(frames0[1])
+    A.preprocess(); B.preprocess()
+    pts = orc.detect_keypoints(A.image, np.zeros((0, 2)), 150, 20.0)[0]
+    pts = np.concatenate([pts, [[5., 5.], [751., 479.], [-30., 100.], [760., 300.], [375.5, 240.25]]], 0)
+    pred = stream0.predict(0, pts)
+    PA, PB = orc.Pyramid(A.image), orc.Pyramid(B.image)
+    for p in (pred, None):
+        n_cv, s_cv = A.track_keypoints(B, pts, p)
+        n_or, s_or, _ = orc.track_keypoints(PA, PB, pts, p)
+        assert (s_cv == s_or).mean() >= 0.995
+        ok = (s_cv != 0) & (s_or != 0)
+        assert ok.sum() > 100 and np.abs(n_cv[ok] - n_or[ok]).max() <= 0.01
