@@ -107,12 +107,16 @@ __device__ __forceinline__ unsigned float_to_u8_rn(float v) {
 __global__ void __launch_bounds__(256)
 clahe_apply_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int src_vec4, ClaheParams cp,
                    ApplyBands bands, const uint8_t *__restrict__ lut, Pyramid pyr, SlotList slots) {
-    extern __shared__ uint32_t comb[];          // [tiles_x + 1][256]: (l11, l12, l21, l22)
-    __shared__ int s_xb[kMaxTiles + 2];
-    const int tid = threadIdx.x;
+    extern __shared__ uint32_t smem_u32[];
+    // [tiles_x + 1][256] combined LUT words (l11, l12, l21, l22), then per-column xa (float) and cell index
+    uint32_t *comb = smem_u32;
+    const int ncx = cp.tiles_x + 1;
+    const int Wg = (cp.W + 3) & ~3;
+    float *xa_s = reinterpret_cast<float *>(comb + ncx * 256);          // [Wg]
+    uint32_t *cb_s = reinterpret_cast<uint32_t *>(xa_s + Wg);           // [Wg] column base into comb (cell << 8)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int band = blockIdx.x, b = blockIdx.y;
     const int cy = bands.cy[band], y0 = bands.y0[band], y1 = bands.y1[band];
-    const int ncx = cp.tiles_x + 1;
     const int ty1 = max(cy - 1, 0), ty2 = min(cy, cp.tiles_y - 1);
     const uint8_t *L = lut + (size_t)b * (cp.tiles_x * cp.tiles_y) * 256;
     for (int i = tid; i < ncx * 256; i += 256) {
@@ -122,51 +126,48 @@ clahe_apply_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int src
         const unsigned l21 = L[(ty2 * cp.tiles_x + tx1) * 256 + v], l22 = L[(ty2 * cp.tiles_x + tx2) * 256 + v];
         comb[i] = l11 | (l12 << 8) | (l21 << 16) | (l22 << 24);
     }
-    if (tid < ncx + 1) s_xb[tid] = cp.xb[tid];
+    for (int x = tid; x < Wg; x += 256) {
+        const float txf = (float)x * cp.inv_tw - 0.5f;
+        xa_s[x] = txf - floorf(txf);
+        int c = 0;
+        while (c < ncx - 1 && x >= cp.xb[c + 1]) ++c;                   // interpolation cell (host-built boundaries)
+        cb_s[x] = (uint32_t)c << 8;
+    }
     __syncthreads();
 
     const uint8_t *img = src[b];
     uint8_t *dst = pyr.image_origin(0, slots.v[b]);
     const int dpitch = pyr.lv[0].ipitch;
-    const int groups = (cp.W + 3) >> 2;
-    const int rows = y1 - y0;
-    for (int g = tid; g < groups * rows; g += 256) {
-        const int y = y0 + g / groups;
-        const int x = (g - (g / groups) * groups) << 2;
+    const int groups = Wg >> 2;
+    for (int y = y0 + warp; y < y1; y += 8) {
         const float tyf = (float)y * cp.inv_th - 0.5f;
         const float ya = tyf - floorf(tyf), ya1 = 1.0f - ya;
-        const uint8_t *srow = img + (size_t)y * pitch + x;
-        unsigned px;
-        const int nvalid = min(4, cp.W - x);
-        if (src_vec4 && nvalid == 4) {
-            px = __ldg(reinterpret_cast<const unsigned *>(srow));
-        } else {
-            px = 0;
-            for (int i = 0; i < nvalid; ++i) px |= (unsigned)__ldg(srow + i) << (8 * i);
-        }
-        // interpolation cell of the first pixel of the group
-        int c = (x + (cp.tw >> 1)) / cp.tw;
-        c = min(c, ncx - 1);
-        while (c > 0 && x < s_xb[c]) --c;
-        while (c < ncx - 1 && x >= s_xb[c + 1]) ++c;
-        unsigned out = 0;
+        const uint8_t *srow = img + (size_t)y * pitch;
+        for (int g = lane; g < groups; g += 32) {
+            const int x = g << 2;
+            const int nvalid = min(4, cp.W - x);
+            unsigned px;
+            if (src_vec4 && nvalid == 4) {
+                px = __ldg(reinterpret_cast<const unsigned *>(srow + x));
+            } else {
+                px = 0;
+                for (int i = 0; i < nvalid; ++i) px |= (unsigned)__ldg(srow + x + i) << (8 * i);
+            }
+            const float4 xa4 = *reinterpret_cast<const float4 *>(xa_s + x);
+            const uint4 cb4 = *reinterpret_cast<const uint4 *>(cb_s + x);
+            const float xas[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
+            const unsigned cbs[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
+            unsigned out = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int xi = x + i;
-            while (c < ncx - 1 && xi >= s_xb[c + 1]) ++c;
-            const float txf = (float)xi * cp.inv_tw - 0.5f;
-            const float xa = txf - floorf(txf), xa1 = 1.0f - xa;
-            const unsigned e = comb[(c << 8) + ((px >> (8 * i)) & 255u)];
-            const float l11 = u8_to_float(e & 255u), l12 = u8_to_float((e >> 8) & 255u);
-            const float l21 = u8_to_float((e >> 16) & 255u), l22 = u8_to_float(e >> 24);
-            const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
-            out |= float_to_u8_rn(res) << (8 * i);
-        }
-        uint8_t *drow = dst + (size_t)y * dpitch + x;
-        if (nvalid == 4) {
-            *reinterpret_cast<unsigned *>(drow) = out;
-        } else {
-            for (int i = 0; i < nvalid; ++i) drow[i] = (uint8_t)(out >> (8 * i));
+            for (int i = 0; i < 4; ++i) {
+                const float xa = xas[i], xa1 = 1.0f - xa;
+                const unsigned e = comb[cbs[i] + ((px >> (8 * i)) & 255u)];
+                const float l11 = u8_to_float(e & 255u), l12 = u8_to_float((e >> 8) & 255u);
+                const float l21 = u8_to_float((e >> 16) & 255u), l22 = u8_to_float(e >> 24);
+                const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+                out |= float_to_u8_rn(res) << (8 * i);
+            }
+            store4_with_halo(dst, dpitch, cp.W, cp.H, pyr.win, x, y, out);
         }
     }
 }
@@ -195,7 +196,7 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
             ++bands.nbands;
         }
     dim3 g2(bands.nbands, slots.n);
-    const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t);
+    const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t) + (size_t)((cp.W + 3) & ~3) * 8;
     RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_kernel<<<g2, 256, smem, ctx->stream>>>(d_src, src_pitch, src_vec4, cp, bands,
                                                                                          ctx->lut, ctx->pyr, slots)));
     return 2;

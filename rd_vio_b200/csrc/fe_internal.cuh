@@ -54,6 +54,33 @@ struct Pyramid {
     }
 };
 
+#ifdef __CUDACC__
+// Stores pixels x..x+3 (x % 4 == 0; only those < W) of row y of an image plane whose interior origin is
+// `org`, AND their REFLECT_101 mirror images inside the win-px halo: the producer of a level materialises
+// the halo that cv::buildOpticalFlowPyramid keeps around it (copyMakeBorder, BORDER_REFLECT_101).
+__device__ __forceinline__ void store4_row(uint8_t *r, int W, int win, int x, int nvalid, unsigned v4, bool near_x) {
+    if (nvalid == 4) *reinterpret_cast<unsigned *>(r + x) = v4;
+    else for (int k = 0; k < nvalid; ++k) r[x + k] = (uint8_t)(v4 >> (8 * k));
+    if (near_x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x + k;
+            const uint8_t b = (uint8_t)(v4 >> (8 * k));
+            if (k < nvalid && xx >= 1 && xx <= win) r[-xx] = b;
+            if (k < nvalid && xx >= W - 1 - win && xx <= W - 2) r[2 * (W - 1) - xx] = b;
+        }
+    }
+}
+__device__ __forceinline__ void store4_with_halo(uint8_t *org, int pitch, int W, int H, int win, int x, int y,
+                                                 unsigned v4) {
+    const int nvalid = min(4, W - x);
+    const bool near_x = (x <= win) || (x + 3 >= W - 1 - win);
+    store4_row(org + (ptrdiff_t)y * pitch, W, win, x, nvalid, v4, near_x);
+    if (y >= 1 && y <= win) store4_row(org - (ptrdiff_t)y * pitch, W, win, x, nvalid, v4, near_x);
+    if (y >= H - 1 - win && y <= H - 2) store4_row(org + (ptrdiff_t)(2 * (H - 1) - y) * pitch, W, win, x, nvalid, v4, near_x);
+}
+#endif
+
 // CLAHE launch parameters (host-precomputed so float boundary cases are
 // evaluated once, with the same float expressions as the reference).
 struct ClaheParams {

@@ -19,146 +19,205 @@
 
 namespace rdfe {
 
-constexpr int HT_W = 32, HT_H = 16;                 // output tile
-constexpr int HP_W = HT_W + 6, HP_H = HT_H + 6;     // pixels   (apron 3)
-constexpr int HG_W = HT_W + 4, HG_H = HT_H + 4;     // products (apron 2)
-constexpr int HR_W = HT_W + 2, HR_H = HT_H + 2;     // response (apron 1)
+// Warp-rolling formulation: a warp owns a strip of HR_ROWS output rows x 120 output columns.  Lane l
+// owns 4 adjacent columns (c0 = x0 - 4 + 4l; lanes 0 and 31 are apron) and walks DOWN the strip one
+// pixel row per step, keeping in registers: the Sobel row terms of the last two rows, the gradient
+// products of the last row (float64) and their pair sums, and the responses of the last rows.
+// Horizontal neighbours come from lane+-1 shuffles.  Pixels are read once per row as one aligned
+// 32-bit word per lane straight from the haloed level-0 plane: the materialised REFLECT_101 halo
+// IS Sobel's border extension.  boxFilter however reflects the PRODUCT maps, and a product evaluated
+// on halo pixels differs from the reflected product in two ways, both handled below:
+//   * gx*gy changes sign across a mirrored row or column;
+//   * the 3-tap row smoothing ((k0*p[x-1]) + k1*p[x]) + k0*p[x+1] is not associative, so on the
+//     mirrored columns x = -1 and x = W it is evaluated in mirrored order.
+// All float64 sums are exact (9 terms, exponent spread < 2^29), hence order independent.
+constexpr int HR_ROWS = 40;            // output rows per warp strip
+constexpr int HR_COLS = 120;           // output columns per warp (lanes 1..30)
+constexpr int HW_WARPS = 4;            // warps per CTA
+constexpr int HW_BUF = 128;            // per-warp candidate staging (keys)
+
+__device__ __forceinline__ float byte_f(unsigned w, int k) {
+    // byte k of w as float: build 2^23 + b by PRMT, subtract 2^23 (exact)
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (unsigned)k)) - 8388608.0f;
+}
+__device__ __forceinline__ double shfl_up_d(double v) {
+    return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), 1), __shfl_up_sync(0xffffffffu, __double2loint(v), 1));
+}
+__device__ __forceinline__ double shfl_down_d(double v) {
+    return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), 1), __shfl_down_sync(0xffffffffu, __double2loint(v), 1));
+}
 
 template <bool kFma>
-__global__ void __launch_bounds__(256)
-harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response) {
-    __shared__ float pf[HP_H][HP_W];
-    __shared__ float pa[HG_H][HG_W], pb[HG_H][HG_W], pc[HG_H][HG_W];
-    __shared__ double ha[HG_H][HR_W], hbb[HG_H][HR_W], hc[HG_H][HR_W];
-    __shared__ float R[HR_H][HR_W];
-    __shared__ unsigned s_wcount[8];
-    __shared__ unsigned s_base;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z, slot = slots.v[b];
+__global__ void __launch_bounds__(HW_WARPS * 32)
+harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
+                  int n_items) {
+    __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * HW_WARPS + warp;
+    if (item >= n_items) return;
+    const int b = blockIdx.y, slot = slots.v[b];
     const LevelGeom g = pyr.lv[0];
     const int W = g.w, H = g.h;
-    const uint8_t *src = pyr.image_origin(0, slot);
-    const int ox = blockIdx.x * HT_W, oy = blockIdx.y * HT_H;
-
+    const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * HR_ROWS;
+    const int c0 = x0 - 4 + 4 * lane;                       // first of this lane's 4 columns
+    const uint8_t *org = pyr.image_origin(0, slot);
+    const bool ld_ok = (c0 + 3 <= W + 20) && (c0 >= -20);   // inside the materialised halo
     const double sc = 1.0 / (4.0 * 3.0 * 255.0);
     const float k0 = (float)sc, k1 = (float)(2.0 * sc);
-
-    // pixels, REFLECT_101 at the image border.  Positions whose products/responses lie outside
-    // the image are never consumed un-reflected (see the index mapping below).
-    for (int i = tid; i < HP_H * HP_W; i += 256) {
-        const int r = i / HP_W, c = i - r * HP_W;
-        const int sy = reflect101(oy - 3 + r, H), sx = reflect101(ox - 3 + c, W);
-        pf[r][c] = (float)src[(size_t)sy * g.ipitch + sx];
-    }
-    __syncthreads();
-    // gradient products at (oy-2+r, ox-2+c).  boxFilter reflects the PRODUCT maps at the
-    // border, so a product position outside the image must hold the product of the
-    // reflected position: recompute it there from reflected pixel coordinates.
-    for (int i = tid; i < HG_H * HG_W; i += 256) {
-        const int r = i / HG_W, c = i - r * HG_W;
-        const int gy_ = oy - 2 + r, gx_ = ox - 2 + c;
-        float p00, p01, p02, p10, p12, p20, p21, p22;
-        if (gy_ >= 0 && gy_ < H && gx_ >= 0 && gx_ < W) {
-            p00 = pf[r][c]; p01 = pf[r][c + 1]; p02 = pf[r][c + 2];
-            p10 = pf[r + 1][c]; p12 = pf[r + 1][c + 2];
-            p20 = pf[r + 2][c]; p21 = pf[r + 2][c + 1]; p22 = pf[r + 2][c + 2];
-        } else {
-            const int cy = reflect101(gy_, H), cx = reflect101(gx_, W);
-            const int y0 = reflect101(cy - 1, H), y2 = reflect101(cy + 1, H);
-            const int x0 = reflect101(cx - 1, W), x2 = reflect101(cx + 1, W);
-            const uint8_t *r0 = src + (size_t)y0 * g.ipitch, *r1 = src + (size_t)cy * g.ipitch,
-                          *r2 = src + (size_t)y2 * g.ipitch;
-            p00 = r0[x0]; p01 = r0[cx]; p02 = r0[x2];
-            p10 = r1[x0]; p12 = r1[x2];
-            p20 = r2[x0]; p21 = r2[cx]; p22 = r2[x2];
-        }
-        const float d0 = p02 - p00, d1 = p12 - p10, d2 = p22 - p20;
-        float gx, s0, s2;
-        if (!kFma) {
-            gx = k1 * d1 + k0 * (d0 + d2);
-            s0 = ((k0 * p00) + k1 * p01) + k0 * p02;
-            s2 = ((k0 * p20) + k1 * p21) + k0 * p22;
-        } else {
-            gx = __fmaf_rn(k0, d0 + d2, k1 * d1);
-            s0 = __fmaf_rn(k0, p02, __fmaf_rn(k1, p01, k0 * p00));
-            s2 = __fmaf_rn(k0, p22, __fmaf_rn(k1, p21, k0 * p20));
-        }
-        const float gy = s2 - s0;
-        pa[r][c] = gx * gx;
-        pb[r][c] = gx * gy;
-        pc[r][c] = gy * gy;
-    }
-    __syncthreads();
-    // horizontal 3-sums in float64 at (oy-2+r, ox-1+c)
-    for (int i = tid; i < HG_H * HR_W; i += 256) {
-        const int r = i / HR_W, c = i - r * HR_W;
-        ha[r][c] = ((double)pa[r][c] + (double)pa[r][c + 1]) + (double)pa[r][c + 2];
-        hbb[r][c] = ((double)pb[r][c] + (double)pb[r][c + 1]) + (double)pb[r][c + 2];
-        hc[r][c] = ((double)pc[r][c] + (double)pc[r][c + 1]) + (double)pc[r][c + 2];
-    }
-    __syncthreads();
-    // vertical 3-sums -> response at (oy-1+r, ox-1+c)
-    for (int i = tid; i < HR_H * HR_W; i += 256) {
-        const int r = i / HR_W, c = i - r * HR_W;
-        const float A = (float)((ha[r][c] + ha[r + 1][c]) + ha[r + 2][c]);
-        const float B = (float)((hbb[r][c] + hbb[r + 1][c]) + hbb[r + 2][c]);
-        const float C = (float)((hc[r][c] + hc[r + 1][c]) + hc[r + 2][c]);
-        float v;
-        if (!kFma) v = (A * C - B * B) - (k * (A + C)) * (A + C);
-        else v = (A * C - B * B) - k * ((A + C) * (A + C));
-        const int y = oy - 1 + r, x = ox - 1 + c;
-        // dilate ignores pixels outside the image: make them lose every comparison
-        R[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? v : -INFINITY;
-    }
-    __syncthreads();
-
-    // NMS + emission: 2 pixels per thread (HT_W*HT_H = 512)
-    unsigned long long keys[2];
-    int nk = 0;
-    float tmax = 0.0f;
+    // per-column flags
+    bool mir[4], bflipx[4], cvalid[4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int i = tid + j * 256;
-        const int r = i / HT_W, c = i - r * HT_W;
-        const int y = oy + r, x = ox + c;
-        if (y < H && x < W) {
-            const float v = R[r + 1][c + 1];
-            if (response) response[((size_t)b * H + y) * W + x] = v;
-            tmax = fmaxf(tmax, v);
-            if (v > 0.0f && y >= 1 && y < H - 1 && x >= 1 && x < W - 1) {
-                const float m = fmaxf(fmaxf(fmaxf(R[r][c], R[r][c + 1]), fmaxf(R[r][c + 2], R[r + 1][c])),
-                                      fmaxf(fmaxf(R[r + 1][c + 2], R[r + 2][c]), fmaxf(R[r + 2][c + 1], R[r + 2][c + 2])));
-                if (v >= m)
-                    keys[nk++] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * W + x);
+    for (int i = 0; i < 4; ++i) {
+        const int x = c0 + i;
+        mir[i] = (x == -1) || (x == W);
+        bflipx[i] = (x < 0) || (x >= W);
+        cvalid[i] = (x >= 0) && (x < W);
+    }
+    float dA[4] = {0, 0, 0, 0}, dB[4] = {0, 0, 0, 0};       // d(y-2), d(y-1)
+    float sA[4] = {0, 0, 0, 0}, sB[4] = {0, 0, 0, 0};       // s(y-2), s(y-1)
+    double pa[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0}, pc[4] = {0, 0, 0, 0};   // products of row p-1
+    double ta[4] = {0, 0, 0, 0}, tb[4] = {0, 0, 0, 0}, tc[4] = {0, 0, 0, 0};   // a(p-2)+a(p-1)
+    float Rm[6], Rc[6];                                      // responses of rows q-2 (hmax3 in [1..4]) and q-1 (cols -1..4)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { Rm[i] = -INFINITY; Rc[i] = -INFINITY; }
+    float tmax = 0.0f;
+    int nbuf = 0;                                            // warp-uniform count of staged keys
+    unsigned long long *buf = s_buf[warp];
+
+    auto flush = [&]() {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&det.cand_count[b], (unsigned)nbuf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < nbuf; i += 32) {
+            const unsigned pos = base + i;
+            if (pos < det.cand_cap) det.cand[(size_t)b * det.cand_cap + pos] = buf[i];
+            else atomicExch(det.overflow, 1u);
+        }
+        __syncwarp();
+        nbuf = 0;
+    };
+
+    const int steps = min(HR_ROWS, H - y0) + 6;
+    for (int j = 0; j < steps; ++j) {
+        const int y = y0 - 3 + j;                            // pixel row loaded this step (>= -3, <= H+2)
+        // ---- pixels c0-1 .. c0+4 as floats
+        unsigned w = 0;
+        if (ld_ok) w = *reinterpret_cast<const unsigned *>(org + (ptrdiff_t)y * g.ipitch + c0);
+        const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+        float p[6];
+        p[0] = byte_f(wl, 3);
+        p[1] = byte_f(w, 0); p[2] = byte_f(w, 1); p[3] = byte_f(w, 2); p[4] = byte_f(w, 3);
+        p[5] = byte_f(wr, 0);
+        // ---- Sobel row terms of row y
+        float dN[4], sN[4], k0p[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) k0p[i] = k0 * p[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dN[i] = p[i + 2] - p[i];
+            if (!kFma) {
+                const float k1p = k1 * p[i + 1];
+                sN[i] = mir[i] ? ((k0p[i + 2] + k1p) + k0p[i]) : ((k0p[i] + k1p) + k0p[i + 2]);
+            } else {
+                sN[i] = mir[i] ? __fmaf_rn(k0, p[i], __fmaf_rn(k1, p[i + 1], k0p[i + 2]))
+                               : __fmaf_rn(k0, p[i + 2], __fmaf_rn(k1, p[i + 1], k0p[i]));
             }
         }
-    }
-    // frame maximum (positive floats order like unsigned ints)
-    unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(tmax));
-    if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
-    // CTA-aggregated append
-    unsigned wtot = __reduce_add_sync(0xffffffffu, (unsigned)nk);
-    unsigned wpre = (unsigned)nk;
+        // ---- gradient products of row pr = y-1 (needs rows y-2, y-1, y)
+        const int pr = y - 1;
+        const bool bflipy = (pr < 0) || (pr >= H);
+        double na[4], nb[4], nc[4];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned t = __shfl_up_sync(0xffffffffu, wpre, d);
-        if (lane >= d) wpre += t;
+        for (int i = 0; i < 4; ++i) {
+            float gx;
+            if (!kFma) gx = k1 * dB[i] + k0 * (dA[i] + dN[i]);
+            else gx = __fmaf_rn(k0, dA[i] + dN[i], k1 * dB[i]);
+            const float gy = sN[i] - sA[i];
+            float fb = gx * gy;
+            if (bflipx[i] != bflipy) fb = -fb;
+            na[i] = (double)(gx * gx);
+            nb[i] = (double)fb;
+            nc[i] = (double)(gy * gy);
+        }
+        // ---- vertical 3-sums for row q = pr-1, then horizontal 3-sums, response
+        const int q = pr - 1;
+        double va[6], vb[6], vc[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            va[i + 1] = ta[i] + na[i]; vb[i + 1] = tb[i] + nb[i]; vc[i + 1] = tc[i] + nc[i];
+            ta[i] = pa[i] + na[i]; tb[i] = pb[i] + nb[i]; tc[i] = pc[i] + nc[i];
+            pa[i] = na[i]; pb[i] = nb[i]; pc[i] = nc[i];
+        }
+        va[0] = shfl_up_d(va[4]); vb[0] = shfl_up_d(vb[4]); vc[0] = shfl_up_d(vc[4]);
+        va[5] = shfl_down_d(va[1]); vb[5] = shfl_down_d(vb[1]); vc[5] = shfl_down_d(vc[1]);
+        const bool qvalid = (q >= 0) && (q < H);
+        float Rn[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float A = (float)((va[i] + va[i + 1]) + va[i + 2]);
+            const float B = (float)((vb[i] + vb[i + 1]) + vb[i + 2]);
+            const float C = (float)((vc[i] + vc[i + 1]) + vc[i + 2]);
+            float v;
+            if (!kFma) v = (A * C - B * B) - (k * (A + C)) * (A + C);
+            else v = (A * C - B * B) - k * ((A + C) * (A + C));
+            Rn[i + 1] = (qvalid && cvalid[i]) ? v : -INFINITY;       // dilate ignores pixels outside the image
+        }
+        Rn[0] = __shfl_up_sync(0xffffffffu, Rn[4], 1);
+        Rn[5] = __shfl_down_sync(0xffffffffu, Rn[1], 1);
+        if (lane == 0) Rn[0] = -INFINITY;
+        if (lane == 31) Rn[5] = -INFINITY;
+        if (response && qvalid && q >= y0 && q < y0 + HR_ROWS && lane >= 1 && lane <= 30) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (cvalid[i]) response[((size_t)b * H + q) * W + c0 + i] = Rn[i + 1];
+        }
+        // ---- NMS for row n = q-1: rows Rm (n-1, already reduced to hmax3), Rc (n), Rn (n+1)
+        const int n = q - 1;
+        unsigned long long key[4];
+        unsigned cmask = 0;
+        const bool nrow_ok = (n >= y0) && (n < y0 + HR_ROWS) && (n >= 1) && (n < H - 1) && lane >= 1 && lane <= 30;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float hn = fmaxf(fmaxf(Rn[i], Rn[i + 1]), Rn[i + 2]);
+            const float v = Rc[i + 1];
+            const float m = fmaxf(fmaxf(Rm[i + 1], hn), fmaxf(Rc[i], Rc[i + 2]));
+            const int x = c0 + i;
+            if (nrow_ok && v > 0.0f && v >= m && x >= 1 && x < W - 1) {
+                cmask |= 1u << i;
+                key[i] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(n * W + x);
+            }
+            if (n >= y0 && n < y0 + HR_ROWS && lane >= 1 && lane <= 30) tmax = fmaxf(tmax, v);   // -inf outside the image never wins
+        }
+        // roll the response rows: Rm <- hmax3(Rc), Rc <- Rn
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Rm[i + 1] = fmaxf(fmaxf(Rc[i], Rc[i + 1]), Rc[i + 2]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Rc[i] = Rn[i];
+        // ---- stage candidates (warp-aggregated, no atomics until a flush)
+        const int mine = __popc(cmask);
+        if (__any_sync(0xffffffffu, mine != 0)) {
+            int pre = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += t;
+            }
+            const int tot = __shfl_sync(0xffffffffu, pre, 31);
+            if (nbuf + tot > HW_BUF) flush();
+            int pos = nbuf + pre - mine;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (cmask & (1u << i)) buf[pos++] = key[i];
+            nbuf += tot;
+            __syncwarp();
+        }
+        // ---- roll the row terms
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dA[i] = dB[i]; dB[i] = dN[i]; sA[i] = sB[i]; sB[i] = sN[i]; }
     }
-    wpre -= (unsigned)nk;
-    if (lane == 0) s_wcount[warp] = wtot;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned tot = 0;
-        for (int w = 0; w < 8; ++w) { unsigned t = s_wcount[w]; s_wcount[w] = tot; tot += t; }
-        s_base = tot ? atomicAdd(&det.cand_count[b], tot) : 0u;
-    }
-    __syncthreads();
-    unsigned pos = s_base + s_wcount[warp] + wpre;
-    for (int j = 0; j < nk; ++j, ++pos) {
-        if (pos < det.cand_cap) det.cand[(size_t)b * det.cand_cap + pos] = keys[j];
-        else atomicExch(det.overflow, 1u);
-    }
+    if (nbuf) flush();
+    const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
+    if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
 }
 
 __global__ void detect_reset_kernel(DetectScratch det, int n) {
@@ -169,11 +228,13 @@ __global__ void detect_reset_kernel(DetectScratch det, int n) {
 int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_response) {
     const LevelGeom &g = ctx->pyr.lv[0];
     detect_reset_kernel<<<1, RDFE_MAX_BATCH, 0, ctx->stream>>>(ctx->det, slots.n);
-    dim3 grid((g.w + HT_W - 1) / HT_W, (g.h + HT_H - 1) / HT_H, slots.n);
+    const int tiles_x = (g.w + HR_COLS - 1) / HR_COLS, strips = (g.h + HR_ROWS - 1) / HR_ROWS;
+    const int n_items = tiles_x * strips;
+    dim3 grid((n_items + HW_WARPS - 1) / HW_WARPS, slots.n);
     if (p.harris_fma)
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
     else
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
     return 2;
 }
 

@@ -2,123 +2,179 @@
 // withDerivatives=true) produces (reference call site: OpenCvImage::preprocess,
 // src/rdvio_extra/src/opencv_image.cpp:159-160; arithmetic: SURVEY.md App. A2-A3).
 //
-//   pyrdown_kernel   level l -> l+1, separable [1 4 6 4 1]^2, (sum+128)>>8, REFLECT_101.
-//   scharr_kernel    all levels in one launch: un-normalised 3x3 Scharr, (dx,dy) int16 pairs.
-//   halo_kernel      all levels in one launch: materialises the win-px REFLECT_101 halo
-//                    around every image plane (the LK window reads it; the derivative
-//                    planes need no halo: TMA out-of-bounds fill supplies their zeros).
+//   pyrdown_kernel   level l -> l+1: separable [1 4 6 4 1]^2, (sum+128)>>8.  A warp owns a strip of
+//                    128 output columns and walks down the INPUT rows: each lane reads one aligned
+//                    8-byte word per row (its 4 output pixels' 8 centre/odd taps), takes the 3 taps it
+//                    lacks from lane+-1 by shuffle, keeps the horizontal sums of the last 5 input rows
+//                    in registers and emits one output row every second step as a 4-byte store
+//                    (128 B per warp).  The producer also writes the output level's win-px
+//                    REFLECT_101 halo (store4_with_halo), so no separate halo pass exists.
+//   scharr_kernel    all levels in one launch, same rolling scheme (4 pixels per lane, 3-row window):
+//                    un-normalised 3x3 Scharr, (dx,dy) int16 pairs, one 16-byte store per lane per row.
+// Both read their border taps from the materialised REFLECT_101 halo of the source level -- exactly the
+// border rule of pyrDown / calcSharrDeriv -- so the inner loops contain no index reflection.
 // All integer arithmetic: bit-exact by construction.
 #include "fe_internal.cuh"
 
 namespace rdfe {
 
-// ---------------------------------------------------------------- pyrDown
-constexpr int PD_TW = 64, PD_TH = 16;             // output tile
-constexpr int PD_IW = 2 * PD_TW + 3, PD_IH = 2 * PD_TH + 3;
+constexpr int PW_WARPS = 4;            // warps per CTA (independent strips)
 
-__global__ void __launch_bounds__(256)
-pyrdown_kernel(Pyramid pyr, SlotList slots, int l) {
-    __shared__ uint8_t in[PD_IH][PD_IW + 1];
-    __shared__ uint16_t hb[PD_IH][PD_TW];
-    const int tid = threadIdx.x;
-    const int slot = slots.v[blockIdx.z];
+__device__ __forceinline__ unsigned bfe8(unsigned w, int k) { return (w >> (8 * k)) & 0xFFu; }
+
+// ---------------------------------------------------------------- pyrDown
+constexpr int PD_ROWS = 8;             // output rows per warp strip
+
+__global__ void __launch_bounds__(PW_WARPS * 32)
+pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * PW_WARPS + warp;
+    if (item >= n_items) return;
+    const int slot = slots.v[blockIdx.y];
     const LevelGeom gs = pyr.lv[l], gd = pyr.lv[l + 1];
     const uint8_t *src = pyr.image_origin(l, slot);
     uint8_t *dst = pyr.image_origin(l + 1, slot);
-    const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
-    const int sx0 = 2 * ox - 2, sy0 = 2 * oy - 2;
+    const int j0 = (item % tiles_x) * 128 + 4 * lane;       // first of this lane's 4 output columns
+    const int i0 = (item / tiles_x) * PD_ROWS;              // first output row of the strip
+    const int rows = min(PD_ROWS, gd.h - i0);
+    const int sx = 2 * j0;                                   // input column of this lane's 8-byte word
+    const bool active = j0 < gd.w;
+    // input columns sx-2 .. sx+8 are needed; all inside [-2, w+1] for active lanes (halo >= 2 px)
+    const bool ld_ok = (sx + 7 <= gs.w + pyr.win - 1);       // also the first inactive lane: its taps feed lane-1
+    const bool edge_l = (lane == 0), edge_r = (lane == 31);
 
-    for (int i = tid; i < PD_IH * PD_IW; i += 256) {
-        const int r = i / PD_IW, c = i - r * PD_IW;
-        const int sy = reflect101(sy0 + r, gs.h), sx = reflect101(sx0 + c, gs.w);
-        in[r][c] = src[(size_t)sy * gs.ipitch + sx];
-    }
-    __syncthreads();
-    for (int i = tid; i < PD_IH * PD_TW; i += 256) {
-        const int r = i / PD_TW, c = i - r * PD_TW;
-        const uint8_t *p = &in[r][2 * c];
-        hb[r][c] = (uint16_t)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
-    }
-    __syncthreads();
-    for (int i = tid; i < PD_TH * PD_TW; i += 256) {
-        const int r = i / PD_TW, c = i - r * PD_TW;
-        const int x = ox + c, y = oy + r;
-        if (x < gd.w && y < gd.h) {
-            const int v = hb[2 * r][c] + 4 * hb[2 * r + 1][c] + 6 * hb[2 * r + 2][c] + 4 * hb[2 * r + 3][c] +
-                          hb[2 * r + 4][c];
-            dst[(size_t)y * gd.ipitch + x] = (uint8_t)((v + 128) >> 8);
+    int h0[4], h1[4], h2[4], h3[4];                          // horizontal sums of input rows y-4 .. y-1
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h0[k] = h1[k] = h2[k] = h3[k] = 0;
+
+    const int ystart = 2 * i0 - 2, nsteps = 2 * rows + 3;    // input rows 2*i0-2 .. 2*(i0+rows-1)+2
+    // software pipelining: the words of step s+1 are requested before step s is consumed
+    const bool el = edge_l && active, er = edge_r && active && (sx + 8 <= gs.w + pyr.win - 4);
+    auto load_row = [&](int y, uint2 &w, unsigned &xl, unsigned &xr) {
+        const uint8_t *row = src + (ptrdiff_t)y * gs.ipitch;
+        w = make_uint2(0u, 0u);
+        xl = 0u; xr = 0u;
+        if (ld_ok) w = *reinterpret_cast<const uint2 *>(row + sx);
+        if (el) xl = *reinterpret_cast<const unsigned *>(row + sx - 4);
+        if (er) xr = *reinterpret_cast<const unsigned *>(row + sx + 8);
+    };
+    uint2 wn; unsigned xln, xrn;
+    load_row(ystart, wn, xln, xrn);
+    for (int s = 0; s < nsteps; ++s) {
+        const uint2 w = wn;
+        const unsigned xl = xln, xr = xrn;
+        if (s + 1 < nsteps) load_row(ystart + s + 1, wn, xln, xrn);
+        unsigned wl = __shfl_up_sync(0xffffffffu, w.y, 1);   // columns sx-4 .. sx-1
+        unsigned wr = __shfl_down_sync(0xffffffffu, w.x, 1); // columns sx+8 .. sx+11
+        if (el) wl = xl;
+        if (er) wr = xr;
+        // taps: p[-2..8] relative to sx
+        unsigned p[11];
+        p[0] = bfe8(wl, 2); p[1] = bfe8(wl, 3);
+        p[2] = bfe8(w.x, 0); p[3] = bfe8(w.x, 1); p[4] = bfe8(w.x, 2); p[5] = bfe8(w.x, 3);
+        p[6] = bfe8(w.y, 0); p[7] = bfe8(w.y, 1); p[8] = bfe8(w.y, 2); p[9] = bfe8(w.y, 3);
+        p[10] = bfe8(wr, 0);
+        int hn[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            hn[k] = (int)(p[2 * k] + p[2 * k + 4] + 4u * (p[2 * k + 1] + p[2 * k + 3]) + 6u * p[2 * k + 2]);
+        if (s >= 4 && (s & 1) == 0) {
+            // input row y = 2i+2  =>  output row i = (y-2)/2
+            const int i = i0 + ((s - 4) >> 1);
+            unsigned out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = h0[k] + hn[k] + 4 * (h1[k] + h3[k]) + 6 * h2[k];
+                out |= (unsigned)((v + 128) >> 8) << (8 * k);
+            }
+            if (active) store4_with_halo(dst, gd.ipitch, gd.w, gd.h, pyr.win, j0, i, out);
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { h0[k] = h1[k]; h1[k] = h2[k]; h2[k] = h3[k]; h3[k] = hn[k]; }
     }
 }
 
 // ----------------------------------------------------------------- Scharr
-constexpr int SC_TW = 64, SC_TH = 16;
+constexpr int SC_ROWS = 16;            // output rows per warp strip
 
-struct TileTable {
-    int first[RDFE_MAX_LEVELS + 1];   // first flattened tile index of each level
+struct ItemTable {
+    int first[RDFE_MAX_LEVELS + 1];   // first flattened work item of each level
     int tiles_x[RDFE_MAX_LEVELS];
 };
 
-__global__ void __launch_bounds__(256)
-scharr_kernel(Pyramid pyr, SlotList slots, TileTable tt) {
-    __shared__ uint8_t in[SC_TH + 2][SC_TW + 2 + 2];
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(PW_WARPS * 32)
+scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item_g = blockIdx.x * PW_WARPS + warp;
+    if (item_g >= tt.first[pyr.nlevels]) return;
     int l = 0;
-    while (l + 1 < pyr.nlevels && (int)blockIdx.x >= tt.first[l + 1]) ++l;
-    const int t = blockIdx.x - tt.first[l];
-    const int ox = (t % tt.tiles_x[l]) * SC_TW, oy = (t / tt.tiles_x[l]) * SC_TH;
+    while (l + 1 < pyr.nlevels && item_g >= tt.first[l + 1]) ++l;
+    const int item = item_g - tt.first[l];
     const int slot = slots.v[blockIdx.y];
     const LevelGeom g = pyr.lv[l];
     const uint8_t *src = pyr.image_origin(l, slot);
-    int16_t *dst = pyr.deriv_origin(l, slot);
+    uint8_t *dst = reinterpret_cast<uint8_t *>(pyr.deriv_origin(l, slot));
+    const int c0 = (item % tt.tiles_x[l]) * 128 + 4 * lane;
+    const int y0 = (item / tt.tiles_x[l]) * SC_ROWS;
+    const int rows = min(SC_ROWS, g.h - y0);
+    const bool active = c0 < g.w;
+    const bool ld_ok = (c0 + 3 <= g.w + pyr.win - 1);        // inside the halo (also the first inactive lane)
+    const bool edge_l = (lane == 0), edge_r = (lane == 31);
 
-    for (int i = tid; i < (SC_TH + 2) * (SC_TW + 2); i += 256) {
-        const int r = i / (SC_TW + 2), c = i - r * (SC_TW + 2);
-        const int sy = reflect101(oy - 1 + r, g.h), sx = reflect101(ox - 1 + c, g.w);
-        in[r][c] = src[(size_t)sy * g.ipitch + sx];
-    }
-    __syncthreads();
-    for (int i = tid; i < SC_TH * SC_TW; i += 256) {
-        const int r = i / SC_TW, c = i - r * SC_TW;
-        const int x = ox + c, y = oy + r;
-        if (x < g.w && y < g.h) {
-            const int a00 = in[r][c], a01 = in[r][c + 1], a02 = in[r][c + 2];
-            const int a10 = in[r + 1][c], a12 = in[r + 1][c + 2];
-            const int a20 = in[r + 2][c], a21 = in[r + 2][c + 1], a22 = in[r + 2][c + 2];
-            const int gx = 3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20);
-            const int gy = 3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02);
-            short2 o;
-            o.x = (short)gx;
-            o.y = (short)gy;
-            *reinterpret_cast<short2 *>(reinterpret_cast<uint8_t *>(dst) + (size_t)y * g.dpitch + 4 * (size_t)x) = o;
+    int d1A[4], d1B[4], s2A[4], s2B[4];                      // rows y-2, y-1: p(x+1)-p(x-1) and 3p(x-1)+10p(x)+3p(x+1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d1A[k] = d1B[k] = s2A[k] = s2B[k] = 0;
+
+    const bool el = edge_l && active, er = edge_r && active;
+    auto load_row = [&](int y, unsigned &w, unsigned &xl, unsigned &xr) {
+        const uint8_t *row = src + (ptrdiff_t)y * g.ipitch;
+        w = 0u; xl = 0u; xr = 0u;
+        if (ld_ok) w = *reinterpret_cast<const unsigned *>(row + c0);
+        if (el) xl = *reinterpret_cast<const unsigned *>(row + c0 - 4);
+        if (er) xr = *reinterpret_cast<const unsigned *>(row + c0 + 4);
+    };
+    unsigned wn, xln, xrn;
+    load_row(y0 - 1, wn, xln, xrn);
+    for (int s = 0; s < rows + 2; ++s) {
+        const int y = y0 - 1 + s;
+        const unsigned w = wn, xl = xln, xr = xrn;
+        if (s + 1 < rows + 2) load_row(y + 1, wn, xln, xrn);
+        unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+        if (el) wl = xl;
+        if (er) wr = xr;
+        int p[6];
+        p[0] = (int)bfe8(wl, 3);
+        p[1] = (int)bfe8(w, 0); p[2] = (int)bfe8(w, 1); p[3] = (int)bfe8(w, 2); p[4] = (int)bfe8(w, 3);
+        p[5] = (int)bfe8(wr, 0);
+        int d1N[4], s2N[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            d1N[k] = p[k + 2] - p[k];
+            s2N[k] = 3 * (p[k] + p[k + 2]) + 10 * p[k + 1];
         }
+        if (s >= 2) {
+            const int r = y - 1;                              // centre row
+            unsigned o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int gx = 3 * (d1A[k] + d1N[k]) + 10 * d1B[k];
+                const int gy = s2N[k] - s2A[k];
+                o[k] = ((unsigned)gx & 0xFFFFu) | ((unsigned)gy << 16);
+            }
+            if (active) {
+                uint8_t *out = dst + (size_t)r * g.dpitch + 4 * (size_t)c0;
+                if (c0 + 3 < g.w) {
+                    *reinterpret_cast<uint4 *>(out) = make_uint4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c0 + k < g.w) reinterpret_cast<unsigned *>(out)[k] = o[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { d1A[k] = d1B[k]; d1B[k] = d1N[k]; s2A[k] = s2B[k]; s2B[k] = s2N[k]; }
     }
-}
-
-// ------------------------------------------------------------------- halo
-struct HaloTable {
-    int first[RDFE_MAX_LEVELS + 1];   // first flattened halo-pixel block (256 px) of each level
-};
-
-__global__ void __launch_bounds__(256)
-halo_kernel(Pyramid pyr, SlotList slots, HaloTable ht) {
-    int l = 0;
-    while (l + 1 < pyr.nlevels && (int)blockIdx.x >= ht.first[l + 1]) ++l;
-    const int idx = (blockIdx.x - ht.first[l]) * 256 + threadIdx.x;
-    const int slot = slots.v[blockIdx.y];
-    const LevelGeom g = pyr.lv[l];
-    const int win = pyr.win;
-    const int fw = g.w + 2 * win;                       // full (haloed) width
-    const int n_tb = win * fw;                          // top band, bottom band
-    const int n_lr = g.h * win;                         // left band, right band
-    int hx, hy;                                         // halo pixel in interior coordinates
-    if (idx < n_tb) { hy = -win + idx / fw; hx = -win + idx % fw; }
-    else if (idx < 2 * n_tb) { const int j = idx - n_tb; hy = g.h + j / fw; hx = -win + j % fw; }
-    else if (idx < 2 * n_tb + n_lr) { const int j = idx - 2 * n_tb; hy = j / win; hx = -win + j % win; }
-    else if (idx < 2 * n_tb + 2 * n_lr) { const int j = idx - 2 * n_tb - n_lr; hy = j / win; hx = g.w + j % win; }
-    else return;
-    uint8_t *org = pyr.image_origin(l, slot);
-    org[(ptrdiff_t)hy * g.ipitch + hx] = org[(size_t)reflect101(hy, g.h) * g.ipitch + reflect101(hx, g.w)];
 }
 
 int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
@@ -126,27 +182,23 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
     int launches = 0;
     for (int l = 0; l + 1 < pyr.nlevels; ++l) {
         const LevelGeom &gd = pyr.lv[l + 1];
-        dim3 grid((gd.w + PD_TW - 1) / PD_TW, (gd.h + PD_TH - 1) / PD_TH, slots.n);
-        RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(pyr, slots, l)));
+        const int tiles_x = (gd.w + 127) / 128, strips = (gd.h + PD_ROWS - 1) / PD_ROWS;
+        const int n_items = tiles_x * strips;
+        dim3 grid((n_items + PW_WARPS - 1) / PW_WARPS, slots.n);
+        RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(pyr, slots, l, tiles_x, n_items)));
         ++launches;
     }
-    TileTable tt;
-    HaloTable ht;
-    int nt = 0, nh = 0;
+    ItemTable tt;
+    int nt = 0;
     for (int l = 0; l < pyr.nlevels; ++l) {
         const LevelGeom &g = pyr.lv[l];
         tt.first[l] = nt;
-        tt.tiles_x[l] = (g.w + SC_TW - 1) / SC_TW;
-        nt += tt.tiles_x[l] * ((g.h + SC_TH - 1) / SC_TH);
-        ht.first[l] = nh;
-        const int npx = 2 * pyr.win * (g.w + 2 * pyr.win) + 2 * g.h * pyr.win;
-        nh += (npx + 255) / 256;
+        tt.tiles_x[l] = (g.w + 127) / 128;
+        nt += tt.tiles_x[l] * ((g.h + SC_ROWS - 1) / SC_ROWS);
     }
     tt.first[pyr.nlevels] = nt;
-    ht.first[pyr.nlevels] = nh;
-    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3(nt, slots.n), 256, 0, ctx->stream>>>(pyr, slots, tt)));
-    RDFE_LAUNCH(ctx, K_HALO, (halo_kernel<<<dim3(nh, slots.n), 256, 0, ctx->stream>>>(pyr, slots, ht)));
-    return launches + 2;
+    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3((nt + PW_WARPS - 1) / PW_WARPS, slots.n), PW_WARPS * 32, 0, ctx->stream>>>(pyr, slots, tt)));
+    return launches + 1;
 }
 
 }  // namespace rdfe
