@@ -240,13 +240,11 @@ def main_b200(args, wl):
     def step_dev(t):
         k = t % T
         prev, new = slots[t % 2], slots[(t + 1) % 2]
-        N.check(L.rdfe_preprocess_batch_dev(h, new.ctypes.data, S, dptrs[(k + 1) % T], W, 6.0, 8, 8), "preprocess")
         work_xy.copy_(pred_xy[k], non_blocking=True)
         work_cnt.copy_(cnt[k], non_blocking=True)
-        N.check(L.rdfe_track_batch_dev(h, prev.ctypes.data, new.ctypes.data, S, C.byref(tp), vp(curr_xy[k]), vp(work_xy),
-                                       vp(cnt[k]), stride, vp(status)), "track")
-        N.check(L.rdfe_detect_batch_dev(h, new.ctypes.data, S, C.byref(dp), vp(work_xy), vp(work_cnt), stride,
-                                        None, None, None), "detect")
+        N.check(L.rdfe_frontend_step_dev(h, prev.ctypes.data, new.ctypes.data, S, dptrs[(k + 1) % T], W, 6.0, 8, 8,
+                                         C.byref(tp), vp(curr_xy[k]), vp(work_xy), vp(cnt[k]), vp(status),
+                                         C.byref(dp), vp(work_cnt), stride), "frontend_step")
 
     # prime: frame 0 preprocessed into the "prev" slots of step 0
     N.check(L.rdfe_preprocess_batch_dev(h, slots[0].ctypes.data, S, dptrs[0], W, 6.0, 8, 8), "preprocess")

@@ -145,6 +145,18 @@ RDFE_API int rdfe_track_batch_dev(rdfe_ctx *ctx, const int *curr_slots, const in
                          const rdfe_track_params *p, const double *dev_curr_xy, double *dev_next_xy,
                          const int *dev_counts, int stride, char *dev_status);
 
+/* ---- one call per new frame: FeatureTracker::run's plugin sequence (feature_tracker.cpp:32-98) ----
+ * preprocess(new) -> track_keypoints(prev -> new) -> detect_keypoints(new), device pointers, asynchronous.
+ * dev_next_xy [n][stride][2]: prediction in (if tp->has_prediction), tracked result out (status != 0 only),
+ * then used as detect's existing keypoints: dev_kp_counts[i] entries on entry, new corners appended and
+ * dev_kp_counts[i] updated.  prev_slots == NULL (first frame of a stream) skips the tracking stage.
+ * GFTT selection runs on an internal second stream concurrently with LK. */
+RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
+                           const uint8_t *const *dev_images, size_t pitch, double clip_limit, int tiles_x, int tiles_y,
+                           const rdfe_track_params *tp, const double *dev_curr_xy, double *dev_next_xy,
+                           const int *dev_track_counts, char *dev_status, const rdfe_detect_params *dp,
+                           int *dev_kp_counts, int stride);
+
 /* ---- parity / debugging taps (not on the hot path) ---------------------- */
 /* plane: 0 = 8-bit image (w*h bytes), 1 = Scharr derivative (w*h*2 int16),
  * 2 = image with its win-px REFLECT_101 halo ((w+2win)*(h+2win) bytes). */

@@ -233,12 +233,13 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
         CK(cudaMalloc(&pyr.der[l], pyr.lv[l].dslot * cfg->num_slots));
         CK(cudaMemset(pyr.der[l], 0, pyr.lv[l].dslot * cfg->num_slots));
     }
-    ctx->raw_pitch = align_up((size_t)cfg->width, 64);
-    ctx->raw_slot = ctx->raw_pitch * cfg->height;
+    ctx->raw_pitch = align_up((size_t)cfg->width, 4);   // tight: a contiguous host image uploads as ONE 1-D copy
+    ctx->raw_slot = align_up(ctx->raw_pitch * cfg->height, 256);
     CK(cudaMalloc(&ctx->raw, ctx->raw_slot * cfg->num_slots));
     CK(cudaMalloc(&ctx->lut, (size_t)RDFE_MAX_BATCH * kMaxTiles * kMaxTiles * 256));
     ctx->det.cand_cap = (unsigned)((size_t)cfg->width * cfg->height / 2);
     CK(cudaMalloc(&ctx->det.cand, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det.cand2, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->det.cand_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.overflow, sizeof(unsigned)));
@@ -254,6 +255,9 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->d_srcptrs, RDFE_MAX_BATCH * sizeof(uint8_t *)));
     if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->ev_t0));
     CK(cudaEventCreate(&ctx->ev_t1));
     ctx->prof_ev = (cudaEvent_t *)calloc(2 * kProfMax, sizeof(cudaEvent_t));
@@ -272,7 +276,7 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int l = 0; l < RDFE_MAX_LEVELS; ++l) { cudaFree(ctx->pyr.img[l]); cudaFree(ctx->pyr.der[l]); }
     cudaFree(ctx->raw); cudaFree(ctx->lut);
-    cudaFree(ctx->det.cand); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.overflow);
+    cudaFree(ctx->det.cand); cudaFree(ctx->det.cand2); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.overflow);
     cudaFree(ctx->d_xy_a); cudaFree(ctx->d_xy_b); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->d_gftt_xy); cudaFree(ctx->d_gftt_resp); cudaFree(ctx->d_gftt_counts); cudaFree(ctx->d_srcptrs);
     if (ctx->prof_ev) {
@@ -281,6 +285,9 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     }
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx->slot_used);
     delete ctx;
@@ -362,8 +369,11 @@ int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n, const uint8_t 
     for (int i = 0; i < n; ++i) {
         if (!images[i]) { set_error("rdfe_preprocess_batch: image %d is null", i); return RDFE_ERR_INVALID; }
         uint8_t *d = ctx->raw + (size_t)slots[i] * ctx->raw_slot;
-        RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width, (size_t)ctx->cfg.height,
-                                       cudaMemcpyHostToDevice, ctx->stream));
+        if (pitch == ctx->raw_pitch)
+            RDFE_CUDA_OK(cudaMemcpyAsync(d, images[i], pitch * (size_t)ctx->cfg.height, cudaMemcpyHostToDevice, ctx->stream));
+        else
+            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width, (size_t)ctx->cfg.height,
+                                           cudaMemcpyHostToDevice, ctx->stream));
         dptr[i] = d;
     }
     rc = rdfe_preprocess_batch_dev(ctx, slots, n, dptr.data(), ctx->raw_pitch, clip_limit, tiles_x, tiles_y);
@@ -470,6 +480,44 @@ int rdfe_track_batch(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots
     return RDFE_OK;
 }
 
+// ------------------------------------------------- fused per-frame step
+// FeatureTracker::run's plugin calls for one new frame per stream (feature_tracker.cpp:32-98) in ONE call:
+// preprocess(new) -> track(prev->new) -> detect(new, existing = tracked positions).  The GFTT selection
+// (which does not depend on the tracked points) runs on the auxiliary stream concurrently with LK; only the
+// Poisson-disk append waits for both.
+int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
+                           const uint8_t *const *dev_images, size_t pitch, double clip_limit, int tiles_x, int tiles_y,
+                           const rdfe_track_params *tp, const double *dev_curr_xy, double *dev_next_xy,
+                           const int *dev_track_counts, char *dev_status, const rdfe_detect_params *dp,
+                           int *dev_kp_counts, int stride) {
+    SlotList sn, spv;
+    int rc = check_slots(ctx, new_slots, n, &sn, "rdfe_frontend_step_dev(new)");
+    if (rc) return rc;
+    if (prev_slots) {
+        rc = check_slots(ctx, prev_slots, n, &spv, "rdfe_frontend_step_dev(prev)");
+        if (rc) return rc;
+        if (!tp || !dev_curr_xy || !dev_track_counts || !dev_status) { set_error("rdfe_frontend_step_dev: null track argument"); return RDFE_ERR_INVALID; }
+    }
+    if (!dev_next_xy || !dev_kp_counts) { set_error("rdfe_frontend_step_dev: null keypoint buffers"); return RDFE_ERR_INVALID; }
+    rc = check_detect(ctx, dp, stride, "rdfe_frontend_step_dev");
+    if (rc) return rc;
+    rc = rdfe_preprocess_batch_dev(ctx, new_slots, n, dev_images, pitch, clip_limit, tiles_x, tiles_y);
+    if (rc) return rc;
+    rc = check_launch(ctx, launch_harris_candidates(ctx, sn, *dp, nullptr), "harris");
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    rc = check_launch(ctx, launch_gftt_select(ctx, ctx->aux_stream, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_resp, ctx->d_gftt_counts), "select");
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    if (prev_slots) {
+        rc = check_launch(ctx, launch_lk(ctx, spv, sn, *tp, dev_curr_xy, dev_next_xy, dev_track_counts, stride, dev_status), "lk");
+        if (rc) return rc;
+    }
+    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return check_launch(ctx, launch_poisson_append(ctx, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_counts, dev_next_xy, dev_kp_counts, stride), "poisson");
+}
+
 // ------------------------------------------------------------ parity taps
 int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst, size_t dst_bytes) {
     if (!ctx || !dst || slot < 0 || slot >= ctx->cfg.num_slots || level < 0 || level >= ctx->pyr.nlevels) {
@@ -570,7 +618,7 @@ int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t b
 }
 
 static const char *const kKernelNames[K_COUNT] = {"clahe_hist_lut", "clahe_apply", "pyrdown", "scharr", "halo",
-                                                  "harris_nms", "select", "lk_track"};
+                                                  "harris_nms", "select", "lk_track", "poisson_append"};
 
 int rdfe_profile_num_kernels(void) { return K_COUNT; }
 const char *rdfe_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }

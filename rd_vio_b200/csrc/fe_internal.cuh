@@ -97,12 +97,13 @@ struct ClaheParams {
 };
 
 enum KernelId {
-    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HALO, K_HARRIS, K_SELECT, K_LK, K_COUNT
+    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HALO, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_COUNT
 };
 constexpr int kProfMax = 4096;      // timed launches between two rdfe_profile_collect calls
 
 struct DetectScratch {
     unsigned long long *cand;     // [RDFE_MAX_BATCH][cand_cap] keys: (float bits << 32) | pixel address
+    unsigned long long *cand2;    // same size: ping-pong buffer for the per-round compaction in select_kernel
     unsigned *cand_count;         // [RDFE_MAX_BATCH]
     unsigned *frame_max;          // [RDFE_MAX_BATCH] max response bits (responses <= 0 never win)
     unsigned *overflow;           // [1]
@@ -120,6 +121,8 @@ struct rdfe_ctx {
     CUtensorMap tm_der[RDFE_MAX_LEVELS];
     cudaStream_t stream;
     bool own_stream;
+    cudaStream_t aux_stream;      // GFTT selection overlaps LK here (rdfe_frontend_step*)
+    cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_t0, ev_t1;
     // scratch
     uint8_t *lut;                 // [RDFE_MAX_BATCH][tiles][256]
@@ -182,6 +185,10 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
                              float *d_response /* optional [n][H][W] */);
 int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, double *d_xy, int *d_counts,
                   int stride, float *d_gftt_xy, float *d_gftt_resp, int *d_gftt_counts);
+int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_detect_params &p, float *d_gftt_xy,
+                       float *d_gftt_resp, int *d_gftt_counts);
+int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, const float *d_gftt_xy,
+                          const int *d_gftt_counts, double *d_xy, int *d_counts, int stride);
 int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const rdfe_track_params &p,
               const double *d_curr_xy, double *d_next_xy, const int *d_counts, int stride, char *d_status);
 

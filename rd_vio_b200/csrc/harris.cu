@@ -40,6 +40,16 @@ __device__ __forceinline__ float byte_f(unsigned w, int k) {
     // byte k of w as float: build 2^23 + b by PRMT, subtract 2^23 (exact)
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (unsigned)k)) - 8388608.0f;
 }
+// float -> double for values that are zero or normal (gradient products are never subnormal: a non-zero
+// Sobel term is >= 1 ulp of an O(1e-3..1) float).  Pure integer re-biasing on the ALU pipe: the F2F
+// conversion unit (XU, ~4 results/clk/SM measured) is the bottleneck of this kernel.
+__device__ __forceinline__ double f2d_exact(float f) {
+    const unsigned u = __float_as_uint(f);
+    const unsigned mag = u & 0x7FFFFFFFu;
+    unsigned hi = (u & 0x80000000u) | ((mag >> 3) + 0x38000000u);
+    if (mag == 0u) hi = u;
+    return __hiloint2double((int)hi, (int)(u << 29));
+}
 __device__ __forceinline__ double shfl_up_d(double v) {
     return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), 1), __shfl_up_sync(0xffffffffu, __double2loint(v), 1));
 }
@@ -98,11 +108,16 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
     };
 
     const int steps = min(HR_ROWS, H - y0) + 6;
+    // software pipelining: the pixel words of rows j+1, j+2 are in flight while row j is processed
+    const uint8_t *rowp = org + (ptrdiff_t)(y0 - 3) * g.ipitch + c0;
+    unsigned wq0 = 0, wq1 = 0;
+    if (ld_ok) { wq0 = *reinterpret_cast<const unsigned *>(rowp); wq1 = *reinterpret_cast<const unsigned *>(rowp + g.ipitch); }
     for (int j = 0; j < steps; ++j) {
-        const int y = y0 - 3 + j;                            // pixel row loaded this step (>= -3, <= H+2)
+        const int y = y0 - 3 + j;                            // pixel row consumed this step (>= -3, <= H+2)
         // ---- pixels c0-1 .. c0+4 as floats
-        unsigned w = 0;
-        if (ld_ok) w = *reinterpret_cast<const unsigned *>(org + (ptrdiff_t)y * g.ipitch + c0);
+        const unsigned w = wq0;
+        wq0 = wq1;
+        if (ld_ok && j + 2 < steps) wq1 = *reinterpret_cast<const unsigned *>(rowp + (ptrdiff_t)(j + 2) * g.ipitch);
         const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
         float p[6];
         p[0] = byte_f(wl, 3);

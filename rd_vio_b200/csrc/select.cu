@@ -41,8 +41,8 @@ __device__ __forceinline__ bool poisson_block_hit(int dcx, int dcy, int span) {
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__restrict__ kp_xy, int *__restrict__ kp_counts,
-              float *__restrict__ gftt_xy, float *__restrict__ gftt_resp, int *__restrict__ gftt_counts) {
+select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, float *__restrict__ gftt_resp,
+              int *__restrict__ gftt_counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *batch = reinterpret_cast<unsigned long long *>(smem_raw);          // [SEL_CAP]
     unsigned *hist = reinterpret_cast<unsigned *>(batch + SEL_CAP);                         // [256]
@@ -51,10 +51,6 @@ select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__rest
     float *ar = ay + sp.cap_k;
     int *anext = reinterpret_cast<int *>(ar + sp.cap_k);
     int *head = anext + sp.cap_k;                                                           // [gw*gh]
-    int *pcx = head + sp.gw * sp.gh;                                                        // [stride]
-    int *pcy = pcx + sp.stride;
-    unsigned char *pflag = reinterpret_cast<unsigned char *>(pcy + sp.stride);              // [stride] visible presets
-    unsigned char *cflag = pflag + sp.stride;                                               // [cap_k] candidate rejected
 
     __shared__ unsigned s_count, s_nb;
     __shared__ unsigned long long s_prefix, s_hi;
@@ -64,7 +60,6 @@ select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__rest
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
     const unsigned n = min(det.cand_count[b], det.cand_cap);
-    const unsigned long long *keys = det.cand + (size_t)b * det.cand_cap;
     const float maxv = __uint_as_float(det.frame_max[b]);
     const float thr = (float)((double)maxv * sp.quality);
     const unsigned thr_bits = __float_as_uint(thr);       // thr >= 0 here (maxv >= 0)
@@ -78,21 +73,59 @@ select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__rest
     const int addr_bits = 32 - __clz(max(sp.W * sp.H - 1, 1));
     const int low_passes = (addr_bits + 7) / 8;
 
+    // The candidate list is re-compacted at the start of every round: keys that are not eligible any more
+    // (R <= thr, already visited) or that lie within minDistance of an already accepted corner can never be
+    // accepted later (the accepted set only grows), so dropping them in parallel is exact and shrinks the
+    // sequential part to the few candidates that still matter.
+    unsigned long long *bufA = det.cand + (size_t)b * det.cand_cap;
+    unsigned long long *bufB = det.cand2 + (size_t)b * det.cand_cap;
+    const unsigned long long *src = bufA;
+    unsigned ncur = n;
+    int round = 0;
     while (true) {
         const unsigned long long hi = s_hi;
-        // ---- count eligible keys (R > thr, key < hi)
+        const int nacc0 = s_naccepted;
         if (tid == 0) s_count = 0;
         __syncthreads();
-        unsigned cnt = 0;
-        for (unsigned i = tid; i < n; i += SEL_THREADS) {
-            const unsigned long long k = keys[i];
-            cnt += ((unsigned)(k >> 32) > thr_bits && k < hi) ? 1u : 0u;
+        unsigned long long *dst = (round & 1) ? bufA : bufB;
+        for (unsigned base = warp * 32; base < ncur; base += SEL_THREADS) {
+            const unsigned i = base + lane;
+            unsigned long long k = 0;
+            bool ok = false;
+            if (i < ncur) {
+                k = src[i];
+                ok = (unsigned)(k >> 32) > thr_bits && k < hi;
+            }
+            if (ok && sp.use_min_dist && nacc0 > 0) {
+                const unsigned addr = (unsigned)k;
+                const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
+                const float fx = (float)x, fy = (float)y;
+                const int xc = x / sp.cell, yc = y / sp.cell;
+                const int x1 = max(xc - 1, 0), y1 = max(yc - 1, 0);
+                const int x2 = min(xc + 1, sp.gw - 1), y2 = min(yc + 1, sp.gh - 1);
+                for (int yy = y1; yy <= y2 && ok; ++yy)
+                    for (int xx = x1; xx <= x2 && ok; ++xx)
+                        for (int j = head[yy * sp.gw + xx]; j >= 0; j = anext[j]) {
+                            const float dx = fx - ax[j], dy = fy - ay[j];
+                            if (dx * dx + dy * dy < sp.min_dist2) { ok = false; break; }
+                        }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m) {
+                unsigned pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_count, (unsigned)__popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                if (ok) dst[pos] = k;
+            }
         }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0 && cnt) atomicAdd(&s_count, cnt);
         __syncthreads();
         const unsigned n_el = s_count;
+        src = dst;
+        ncur = n_el;
+        ++round;
         if (n_el == 0) break;
+        const unsigned n = ncur;                      // every key of the compacted list is eligible
+        const unsigned long long *keys = src;
 
         // ---- exact radix select of the SEL_CAP-th largest eligible key
         unsigned long long lo = 0;
@@ -107,7 +140,7 @@ select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__rest
                 const unsigned long long prefix = s_prefix;
                 for (unsigned i = tid; i < n; i += SEL_THREADS) {
                     const unsigned long long k = keys[i];
-                    if ((unsigned)(k >> 32) > thr_bits && k < hi && (k & mask) == prefix)
+                    if ((k & mask) == prefix)
                         atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
                 }
                 __syncthreads();
@@ -147,7 +180,7 @@ select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__rest
         __syncthreads();
         for (unsigned i = tid; i < n; i += SEL_THREADS) {
             const unsigned long long k = keys[i];
-            if ((unsigned)(k >> 32) > thr_bits && k < hi && k >= lo) {
+            if (k >= lo) {
                 const unsigned pos = atomicAdd(&s_nb, 1u);
                 if (pos < SEL_CAP) batch[pos] = k;
             }
@@ -227,64 +260,115 @@ select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__rest
     __syncthreads();
 
     const int na = s_naccepted;
-    if (gftt_counts && tid == 0) gftt_counts[b] = na;
-    if (gftt_xy)
-        for (int i = tid; i < na; i += SEL_THREADS) {
-            gftt_xy[((size_t)b * sp.cap_k + i) * 2] = ax[i];
-            gftt_xy[((size_t)b * sp.cap_k + i) * 2 + 1] = ay[i];
-            if (gftt_resp) gftt_resp[(size_t)b * sp.cap_k + i] = ar[i];
-        }
-    if (!kp_xy) return;
+    if (tid == 0) gftt_counts[b] = na;
+    for (int i = tid; i < na; i += SEL_THREADS) {
+        gftt_xy[((size_t)b * sp.cap_k + i) * 2] = ax[i];
+        gftt_xy[((size_t)b * sp.cap_k + i) * 2 + 1] = ay[i];
+        gftt_resp[(size_t)b * sp.cap_k + i] = ar[i];
+    }
+}
 
-    // ---- Poisson-disk filter against the existing keypoints (float64, reference semantics)
+// ---- extra::PoissonDiskFilter<2> + border reject + append (poisson_disk_filter.h:23-94, opencv_image.cpp:57-71).
+// Separate launch: it is the only part of detect that depends on the tracked keypoints, so the GFTT
+// selection above can overlap the LK kernel on another stream.
+constexpr int PO_THREADS = 512;
+
+__global__ void __launch_bounds__(PO_THREADS)
+poisson_append_kernel(SelectParams sp, const float *__restrict__ gftt_xy, const int *__restrict__ gftt_counts,
+                      double *__restrict__ kp_xy, int *__restrict__ kp_counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *pxs = reinterpret_cast<double *>(smem_raw);                                     // [stride] preset x
+    double *pys = pxs + sp.stride;                                                          // [stride] preset y
+    float *ax = reinterpret_cast<float *>(pys + sp.stride);                                 // [cap_k]
+    float *ay = ax + sp.cap_k;
+    int *pcx = reinterpret_cast<int *>(ay + sp.cap_k);                                      // [stride] preset cells
+    int *pcy = pcx + sp.stride;
+    int *ccx_s = pcy + sp.stride;                                                           // [cap_k] candidate cells
+    int *ccy_s = ccx_s + sp.cap_k;
+    int *ins = ccy_s + sp.cap_k;                                                            // [cap_k] inserted candidates
+    unsigned char *pflag = reinterpret_cast<unsigned char *>(ins + sp.cap_k);               // [stride] visible presets
+    unsigned char *cflag = pflag + sp.stride;                                               // [cap_k] candidate rejected
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = PO_THREADS / 32;
+    const int b = blockIdx.x;
+    const int na = min(gftt_counts[b], sp.cap_k);
     double *pts = kp_xy + (size_t)b * sp.stride * 2;
     const int ne = min(kp_counts[b], sp.stride);
     const double radius = sp.kp_radius, r2 = radius * radius;
     const double gsz = radius / sqrt(2.0);
     const int span = (int)ceil(sqrt(2.0));
-    for (int i = tid; i < ne; i += SEL_THREADS) {
-        pcx[i] = (int)floor(pts[2 * i] / gsz);
-        pcy[i] = (int)floor(pts[2 * i + 1] / gsz);
+    // ---- load presets and candidates, compute their grid cells once (float64 division: reference semantics)
+    for (int i = tid; i < ne; i += PO_THREADS) {
+        const double x = pts[2 * i], y = pts[2 * i + 1];
+        pxs[i] = x; pys[i] = y;
+        pcx[i] = (int)floor(x / gsz);
+        pcy[i] = (int)floor(y / gsz);
+        pflag[i] = 1;
+    }
+    for (int c = tid; c < na; c += PO_THREADS) {
+        const float x = gftt_xy[((size_t)b * sp.cap_k + c) * 2], y = gftt_xy[((size_t)b * sp.cap_k + c) * 2 + 1];
+        ax[c] = x; ay[c] = y;
+        ccx_s[c] = (int)floor((double)x / gsz);
+        ccy_s[c] = (int)floor((double)y / gsz);
+        cflag[c] = 0;
     }
     __syncthreads();
-    for (int i = tid; i < ne; i += SEL_THREADS) {
-        bool vis = true;                                 // preset_point: later preset in the same cell overwrites
-        for (int j = i + 1; j < ne; ++j)
-            if (pcx[j] == pcx[i] && pcy[j] == pcy[i]) { vis = false; break; }
-        pflag[i] = vis ? 1 : 0;
+    // ---- preset_point: a later preset in the same cell overwrites (hides) an earlier one
+    for (int j = warp; j < ne; j += NW) {
+        const int jx = pcx[j], jy = pcy[j];
+        for (int i = lane; i < j; i += 32)
+            if (pcx[i] == jx && pcy[i] == jy) pflag[i] = 0;
     }
-    for (int i = tid; i < na; i += SEL_THREADS) cflag[i] = 0;
     __syncthreads();
-    // candidate x preset pairs
-    for (long long t = tid; t < (long long)na * ne; t += SEL_THREADS) {
-        const int c = (int)(t / ne), i = (int)(t - (long long)c * ne);
-        if (!pflag[i]) continue;
+    // ---- candidate x preset pairs: a warp per candidate, lanes over presets
+    for (int c = warp; c < na; c += NW) {
         const double cx = (double)ax[c], cy = (double)ay[c];
-        const int ccx = (int)floor(cx / gsz), ccy = (int)floor(cy / gsz);
-        if (!poisson_block_hit(pcx[i] - ccx, pcy[i] - ccy, span)) continue;
-        const double dx = cx - pts[2 * i], dy = cy - pts[2 * i + 1];
-        if (dx * dx + dy * dy < r2) cflag[c] = 1;
+        const int ccx = ccx_s[c], ccy = ccy_s[c];
+        bool hit = false;
+        for (int i = lane; i < ne; i += 32) {
+            if (!pflag[i]) continue;
+            if (!poisson_block_hit(pcx[i] - ccx, pcy[i] - ccy, span)) continue;
+            const double dx = cx - pxs[i], dy = cy - pys[i];
+            if (dx * dx + dy * dy < r2) hit = true;
+        }
+        if (__any_sync(0xffffffffu, hit) && lane == 0) cflag[c] = 1;
     }
     __syncthreads();
-    // sequential insertion of the survivors (new points also block later ones), border reject, append
-    if (warp == 0) {
-        int nout = ne;          // write cursor in pts
-        int nins = 0;           // inserted candidates are kept compacted in ax/ay[0..nins) -- safe: nins <= c
+    if (warp != 0) return;
+    int nout = ne;              // write cursor in pts
+    if (sp.kp_radius * sp.kp_radius <= (double)sp.min_dist2 && sp.use_min_dist) {
+        // GFTT already keeps its corners >= minDistance apart (integer-exact test), so two NEW points can
+        // never be closer than the Poisson radius: insertion order no longer matters -> parallel compaction.
+        for (int base = 0; base < na; base += 32) {
+            const int c = base + lane;
+            bool keep = false;
+            double cx = 0, cy = 0;
+            if (c < na && !cflag[c]) {
+                cx = (double)ax[c]; cy = (double)ay[c];
+                keep = !(cx < sp.border || cy < sp.border || cx >= sp.W - sp.border || cy >= sp.H - sp.border);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const int pos = nout + __popc(m & ((1u << lane) - 1u));
+            if (keep && pos < sp.stride) { pts[2 * pos] = cx; pts[2 * pos + 1] = cy; }
+            nout = min(nout + __popc(m), sp.stride);
+        }
+    } else {
+        // general radius: sequential insertion (new points also block later ones), border reject, append
+        int nins = 0;
         for (int c = 0; c < na; ++c) {
             if (cflag[c]) continue;                      // warp-uniform (shared memory flag)
             const double cx = (double)ax[c], cy = (double)ay[c];
-            const int ccx = (int)floor(cx / gsz), ccy = (int)floor(cy / gsz);
+            const int ccx = ccx_s[c], ccy = ccy_s[c];
             bool hit = false;
             for (int i = lane; i < nins; i += 32) {
-                const double qx = (double)ax[i], qy = (double)ay[i];
-                const int qcx = (int)floor(qx / gsz), qcy = (int)floor(qy / gsz);
-                if (!poisson_block_hit(qcx - ccx, qcy - ccy, span)) continue;
-                const double dx = cx - qx, dy = cy - qy;
+                const int q = ins[i];
+                if (!poisson_block_hit(ccx_s[q] - ccx, ccy_s[q] - ccy, span)) continue;
+                const double dx = cx - (double)ax[q], dy = cy - (double)ay[q];
                 if (dx * dx + dy * dy < r2) hit = true;
             }
             if (__any_sync(0xffffffffu, hit)) continue;
             __syncwarp();
-            if (lane == 0) { ax[nins] = (float)cx; ay[nins] = (float)cy; }
+            if (lane == 0) ins[nins] = c;
             ++nins;
             __syncwarp();
             const bool out_of_border = cx < sp.border || cy < sp.border || cx >= sp.W - sp.border || cy >= sp.H - sp.border;
@@ -293,14 +377,12 @@ select_kernel(DetectScratch det, SelectParams sp, SlotList slots, double *__rest
                 ++nout;
             }
         }
-        if (lane == 0) kp_counts[b] = nout;
     }
+    if (lane == 0) kp_counts[b] = nout;
 }
 
-int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, double *d_xy, int *d_counts,
-                  int stride, float *d_gftt_xy, float *d_gftt_resp, int *d_gftt_counts) {
+static void fill_select_params(rdfe_ctx *ctx, const rdfe_detect_params &p, int stride, SelectParams &sp) {
     const LevelGeom &g = ctx->pyr.lv[0];
-    SelectParams sp;
     sp.W = g.w; sp.H = g.h;
     sp.max_corners = p.max_points;
     sp.quality = p.quality_level;
@@ -313,8 +395,14 @@ int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params
     sp.border = p.border;
     sp.stride = stride;
     sp.cap_k = p.max_points;
-    const size_t smem = (size_t)SEL_CAP * 8 + 256 * 4 + (size_t)sp.cap_k * 16 + (size_t)sp.gw * sp.gh * 4 +
-                        (size_t)stride * 8 + (size_t)stride + (size_t)sp.cap_k + 64;
+}
+
+// GFTT selection on `stream` (may be the context's auxiliary stream): candidates -> gftt_* arrays
+int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_detect_params &p, float *d_gftt_xy,
+                       float *d_gftt_resp, int *d_gftt_counts) {
+    SelectParams sp;
+    fill_select_params(ctx, p, 1, sp);
+    const size_t smem = (size_t)SEL_CAP * 8 + 256 * 4 + (size_t)sp.cap_k * 16 + (size_t)sp.gw * sp.gh * 4 + 64;
     if (smem > 200 * 1024) {
         set_error("select: shared memory need %zu B exceeds the CTA limit (max_points=%d, grid %dx%d)", smem,
                   p.max_points, sp.gw, sp.gh);
@@ -328,9 +416,40 @@ int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params
         }
         s_attr = smem;
     }
-    RDFE_LAUNCH(ctx, K_SELECT, (select_kernel<<<slots.n, SEL_THREADS, smem, ctx->stream>>>(ctx->det, sp, slots, d_xy, d_counts, d_gftt_xy,
-                                                                                            d_gftt_resp, d_gftt_counts)));
+    const int pi = (stream == ctx->stream) ? prof_begin(ctx, K_SELECT) : -1;
+    select_kernel<<<n, SEL_THREADS, smem, stream>>>(ctx->det, sp, d_gftt_xy, d_gftt_resp, d_gftt_counts);
+    prof_end(ctx, pi);
     return 1;
+}
+
+int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, const float *d_gftt_xy,
+                          const int *d_gftt_counts, double *d_xy, int *d_counts, int stride) {
+    SelectParams sp;
+    fill_select_params(ctx, p, stride, sp);
+    const size_t smem = (size_t)sp.cap_k * 21 + (size_t)stride * 25 + 64;
+    if (smem > 200 * 1024) { set_error("poisson: shared memory need %zu B too large", smem); return RDFE_ERR_UNSUPPORTED; }
+    static size_t s_attr = 0;
+    if (smem > 48 * 1024 && smem > s_attr) {
+        if (cudaFuncSetAttribute(poisson_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            set_error("poisson: cudaFuncSetAttribute(%zu) failed", smem);
+            return RDFE_ERR_CUDA;
+        }
+        s_attr = smem;
+    }
+    RDFE_LAUNCH(ctx, K_POISSON, (poisson_append_kernel<<<n, PO_THREADS, smem, ctx->stream>>>(sp, d_gftt_xy, d_gftt_counts, d_xy, d_counts)));
+    return 1;
+}
+
+int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, double *d_xy, int *d_counts,
+                  int stride, float *d_gftt_xy, float *d_gftt_resp, int *d_gftt_counts) {
+    float *gxy = d_gftt_xy ? d_gftt_xy : ctx->d_gftt_xy;
+    float *gre = d_gftt_resp ? d_gftt_resp : ctx->d_gftt_resp;
+    int *gcn = d_gftt_counts ? d_gftt_counts : ctx->d_gftt_counts;
+    int rc = launch_gftt_select(ctx, ctx->stream, slots.n, p, gxy, gre, gcn);
+    if (rc < 0) return rc;
+    if (!d_xy) return 1;
+    rc = launch_poisson_append(ctx, slots.n, p, gxy, gcn, d_xy, d_counts, stride);
+    return rc < 0 ? rc : 2;
 }
 
 }  // namespace rdfe

@@ -93,7 +93,7 @@ def test_harris_response_bit_exact(orc, fe752, frames0, fma):
         fe752.release(s)
 
 
-@pytest.mark.parametrize("n_existing,radius,max_points", [(0, 20.0, 150), (47, 20.0, 150), (47, 10.0, 200), (0, 20.0, 1)])
+@pytest.mark.parametrize("n_existing,radius,max_points", [(0, 20.0, 150), (47, 20.0, 150), (47, 10.0, 200), (0, 20.0, 1), (47, 30.0, 150), (20, 45.5, 150)])
 def test_detect_identical(orc, fe752, frames0, n_existing, radius, max_points):
     s = _pre(fe752, frames0[1])
     try:
@@ -195,3 +195,54 @@ def test_large_window_config(orc):
         both = (got_st[0] != 0) & (ref_st != 0)
         err = np.abs(got_xy[0][both] - ref_xy[both]).max()
         assert agree >= MIN_STATUS_AGREE and err <= TOL_PX, (agree, err)
+
+
+def test_fused_step_equals_separate_calls(orc, stream0, frames0):
+    """rdfe_frontend_step_dev (GFTT selection overlapped with LK on a second stream) == preprocess + track + detect."""
+    import ctypes as C
+    import torch
+    from rd_vio_b200 import _native as N
+    from rd_vio_b200.frontend import FrontEnd
+    L = N.lib()
+    n, stride = 3, 300
+    ts = torch.cuda.Stream()
+    with torch.cuda.stream(ts):
+        fe = FrontEnd(752, 480, 3, 21, num_slots=2 * n, max_points=512, stream=ts.cuda_stream)
+        prev = np.array([fe.acquire() for _ in range(n)], np.int32)
+        new = np.array([fe.acquire() for _ in range(n)], np.int32)
+        fe.preprocess(list(prev), frames0[0:n])
+        kps = fe.detect(list(prev), [np.zeros((0, 2))] * n, 150, 20.0)
+        preds = [stream0.predict(i, kps[i]) for i in range(n)]
+        # separate calls (host API) as the expectation
+        fe.preprocess(list(new), frames0[1:n + 1])
+        nxt, st = fe.track(list(prev), list(new), kps, preds)
+        want = []
+        for i in range(n):
+            ex = preds[i].copy()
+            ex[st[i] != 0] = nxt[i][st[i] != 0]
+            want.append(fe.detect([int(new[i])], [ex], 150, 20.0, stride=stride)[0])
+        # fused device call
+        curr = torch.zeros((n, stride, 2), dtype=torch.float64)
+        work = torch.zeros((n, stride, 2), dtype=torch.float64)
+        cnt = torch.zeros(n, dtype=torch.int32)
+        for i in range(n):
+            curr[i, :len(kps[i])] = torch.from_numpy(kps[i])
+            work[i, :len(kps[i])] = torch.from_numpy(preds[i])
+            cnt[i] = len(kps[i])
+        curr, work, cnt = curr.cuda(), work.cuda(), cnt.cuda()
+        kcnt = cnt.clone()
+        status = torch.zeros((n, stride), dtype=torch.int8, device="cuda")
+        imgs = torch.from_numpy(np.stack(frames0[1:n + 1])).cuda()
+        ptrs = (C.c_void_p * n)(*[imgs[i].data_ptr() for i in range(n)])
+        tp, dp = fe.track_params(has_prediction=1), fe.detect_params(max_points=150, keypoint_distance=20.0)
+        N.check(L.rdfe_frontend_step_dev(fe.handle, prev.ctypes.data, new.ctypes.data, n, ptrs, 752, 6.0, 8, 8, C.byref(tp),
+                                         C.c_void_p(curr.data_ptr()), C.c_void_p(work.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                         C.c_void_p(status.data_ptr()), C.byref(dp), C.c_void_p(kcnt.data_ptr()), stride),
+                "frontend_step")
+        fe.sync()
+        got_xy, got_cnt, got_st = work.cpu().numpy(), kcnt.cpu().numpy(), status.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got_st[i, :len(kps[i])], st[i])
+            assert got_cnt[i] == len(want[i])
+            assert np.array_equal(got_xy[i, :got_cnt[i]], want[i])
+        fe.close()
