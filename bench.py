@@ -256,12 +256,17 @@ def main_b200(args, wl):
         torch.cuda.synchronize()
 
     t = 0
+    sampler = ClockSampler(local)
+    sampler.start()                      # clocks are sampled under load: warm-up + timed region
+    w0 = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         step_dev(t); t += 1
-    # keep the step parity so prev/new slots stay consistent: warm-up count may be odd, that is fine (t carries on)
-    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    while time.perf_counter() - w0 < 0.8:   # extra untimed warm-up so nvidia-smi (100 ms period) sees the load
+        for _ in range(20):
+            step_dev(t); t += 1
+        torch.cuda.synchronize()
     barrier()
-    sampler.start()
     launches0 = fe.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

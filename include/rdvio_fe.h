@@ -150,7 +150,8 @@ RDFE_API int rdfe_track_batch_dev(rdfe_ctx *ctx, const int *curr_slots, const in
  * dev_next_xy [n][stride][2]: prediction in (if tp->has_prediction), tracked result out (status != 0 only),
  * then used as detect's existing keypoints: dev_kp_counts[i] entries on entry, new corners appended and
  * dev_kp_counts[i] updated.  prev_slots == NULL (first frame of a stream) skips the tracking stage.
- * GFTT selection runs on an internal second stream concurrently with LK. */
+ * After CLAHE the detection branch (Harris + GFTT selection, which need only level 0) runs on an internal second
+ * stream concurrently with the tracking branch (pyramid, Scharr, LK); only the Poisson-disk append joins both. */
 RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
                            const uint8_t *const *dev_images, size_t pitch, double clip_limit, int tiles_x, int tiles_y,
                            const rdfe_track_params *tp, const double *dev_curr_xy, double *dev_next_xy,

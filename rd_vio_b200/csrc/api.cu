@@ -134,6 +134,8 @@ static int check_slots(const rdfe_ctx *ctx, const int *slots, int n, SlotList *o
     return RDFE_OK;
 }
 
+static inline const SlotList &sl_copy(const SlotList &s) { return s; }
+
 static int check_launch(rdfe_ctx *ctx, int launched, const char *what) {
     if (launched < 0) return launched;
     cudaError_t e = cudaGetLastError();
@@ -255,6 +257,8 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->d_srcptrs, RDFE_MAX_BATCH * sizeof(uint8_t *)));
     if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    ctx->ls = ctx->stream;
+    ctx->overlap = true;
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -305,6 +309,7 @@ int rdfe_level_size(const rdfe_ctx *ctx, int level, int *width, int *height) {
 int rdfe_sync(rdfe_ctx *ctx) {
     if (!ctx) return RDFE_ERR_INVALID;
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream));
     unsigned ovf = 0;
     RDFE_CUDA_OK(cudaMemcpy(&ovf, ctx->det.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
     if (ovf) {
@@ -501,20 +506,42 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     if (!dev_next_xy || !dev_kp_counts) { set_error("rdfe_frontend_step_dev: null keypoint buffers"); return RDFE_ERR_INVALID; }
     rc = check_detect(ctx, dp, stride, "rdfe_frontend_step_dev");
     if (rc) return rc;
-    rc = rdfe_preprocess_batch_dev(ctx, new_slots, n, dev_images, pitch, clip_limit, tiles_x, tiles_y);
+    // CLAHE (level 0 + halo) first: both branches need it
+    ClaheParams cp;
+    rc = make_clahe_params(ctx, clip_limit, tiles_x, tiles_y, &cp);
     if (rc) return rc;
+    if (!dev_images || pitch < (size_t)ctx->cfg.width) { set_error("rdfe_frontend_step_dev: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
+    int vec4 = (pitch % 4 == 0) ? 1 : 0;
+    for (int i = 0; i < n; ++i) {
+        if (!dev_images[i]) { set_error("rdfe_frontend_step_dev: image %d is null", i); return RDFE_ERR_INVALID; }
+        if ((uintptr_t)dev_images[i] % 4) vec4 = 0;
+    }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->last_clahe_tiles = tiles_x * tiles_y;
+    rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), ctx->d_srcptrs, pitch, vec4, cp), "clahe");
+    if (rc) return rc;
+    // detection branch (Harris needs only level 0): auxiliary stream, concurrent with pyramid + LK
+    const bool ov = ctx->overlap && !ctx->prof_on;
+    if (ov) {
+        RDFE_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        ctx->ls = ctx->aux_stream;
+    }
     rc = check_launch(ctx, launch_harris_candidates(ctx, sn, *dp, nullptr), "harris");
+    if (rc == RDFE_OK)
+        rc = check_launch(ctx, launch_gftt_select(ctx, ctx->ls, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_resp, ctx->d_gftt_counts), "select");
+    ctx->ls = ctx->stream;
     if (rc) return rc;
-    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-    rc = check_launch(ctx, launch_gftt_select(ctx, ctx->aux_stream, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_resp, ctx->d_gftt_counts), "select");
+    if (ov) RDFE_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    // tracking branch: pyramid levels, Scharr, LK
+    rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
     if (rc) return rc;
-    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     if (prev_slots) {
         rc = check_launch(ctx, launch_lk(ctx, spv, sn, *tp, dev_curr_xy, dev_next_xy, dev_track_counts, stride, dev_status), "lk");
         if (rc) return rc;
     }
-    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (ov) RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     return check_launch(ctx, launch_poisson_append(ctx, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_counts, dev_next_xy, dev_kp_counts, stride), "poisson");
 }
 

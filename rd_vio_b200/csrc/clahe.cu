@@ -176,7 +176,7 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
                  int src_vec4, const ClaheParams &cp) {
     const int ntiles = cp.tiles_x * cp.tiles_y;
     dim3 g1(ntiles, slots.n);
-    RDFE_LAUNCH(ctx, K_CLAHE_HIST, (clahe_hist_lut_kernel<<<g1, kHistWarps * 32, 0, ctx->stream>>>(d_src, src_pitch, cp, ctx->lut)));
+    RDFE_LAUNCH(ctx, K_CLAHE_HIST, (clahe_hist_lut_kernel<<<g1, kHistWarps * 32, 0, ctx->ls>>>(d_src, src_pitch, cp, ctx->lut)));
 
     // row bands: split every interpolation cell row into chunks of <= RB rows
     ApplyBands bands;
@@ -197,7 +197,7 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
         }
     dim3 g2(bands.nbands, slots.n);
     const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t) + (size_t)((cp.W + 3) & ~3) * 8;
-    RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_kernel<<<g2, 256, smem, ctx->stream>>>(d_src, src_pitch, src_vec4, cp, bands,
+    RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_kernel<<<g2, 256, smem, ctx->ls>>>(d_src, src_pitch, src_vec4, cp, bands,
                                                                                          ctx->lut, ctx->pyr, slots)));
     return 2;
 }

@@ -121,7 +121,9 @@ struct rdfe_ctx {
     CUtensorMap tm_der[RDFE_MAX_LEVELS];
     cudaStream_t stream;
     bool own_stream;
-    cudaStream_t aux_stream;      // GFTT selection overlaps LK here (rdfe_frontend_step*)
+    cudaStream_t ls;              // stream the kernel launchers currently enqueue on (stream or aux_stream)
+    bool overlap;                 // rdfe_frontend_step*: run Harris + selection on aux_stream beside pyramid + LK
+    cudaStream_t aux_stream;      // detection branch of rdfe_frontend_step*
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_t0, ev_t1;
     // scratch
@@ -164,11 +166,11 @@ inline int prof_begin(rdfe_ctx *ctx, int kid) {
     if (!ctx->prof_on || ctx->prof_used >= kProfMax) return -1;
     const int i = ctx->prof_used++;
     ctx->prof_kid[i] = kid;
-    cudaEventRecord(ctx->prof_ev[2 * i], ctx->stream);
+    cudaEventRecord(ctx->prof_ev[2 * i], ctx->ls);
     return i;
 }
 inline void prof_end(rdfe_ctx *ctx, int i) {
-    if (i >= 0) cudaEventRecord(ctx->prof_ev[2 * i + 1], ctx->stream);
+    if (i >= 0) cudaEventRecord(ctx->prof_ev[2 * i + 1], ctx->ls);
 }
 #define RDFE_LAUNCH(ctx, KID, ...)                     \
     do {                                               \

@@ -31,7 +31,7 @@ namespace rdfe {
 //   * the 3-tap row smoothing ((k0*p[x-1]) + k1*p[x]) + k0*p[x+1] is not associative, so on the
 //     mirrored columns x = -1 and x = W it is evaluated in mirrored order.
 // All float64 sums are exact (9 terms, exponent spread < 2^29), hence order independent.
-constexpr int HR_ROWS = 40;            // output rows per warp strip
+constexpr int HR_ROWS = 44;            // output rows per warp strip
 constexpr int HR_COLS = 120;           // output columns per warp (lanes 1..30)
 constexpr int HW_WARPS = 4;            // warps per CTA
 constexpr int HW_BUF = 128;            // per-warp candidate staging (keys)
@@ -58,7 +58,7 @@ __device__ __forceinline__ double shfl_down_d(double v) {
 }
 
 template <bool kFma>
-__global__ void __launch_bounds__(HW_WARPS * 32)
+__global__ void __launch_bounds__(HW_WARPS * 32, 4)
 harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
                   int n_items) {
     __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
@@ -242,14 +242,14 @@ __global__ void detect_reset_kernel(DetectScratch det, int n) {
 
 int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_response) {
     const LevelGeom &g = ctx->pyr.lv[0];
-    detect_reset_kernel<<<1, RDFE_MAX_BATCH, 0, ctx->stream>>>(ctx->det, slots.n);
+    detect_reset_kernel<<<1, RDFE_MAX_BATCH, 0, ctx->ls>>>(ctx->det, slots.n);
     const int tiles_x = (g.w + HR_COLS - 1) / HR_COLS, strips = (g.h + HR_ROWS - 1) / HR_ROWS;
     const int n_items = tiles_x * strips;
     dim3 grid((n_items + HW_WARPS - 1) / HW_WARPS, slots.n);
     if (p.harris_fma)
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
     else
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->stream>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
     return 2;
 }
 

@@ -29,11 +29,11 @@ namespace rdfe {
 
 template <int WIN> struct LKCfg;
 template <> struct LKCfg<21> {
-    static constexpr int SEG = 7, NSEG = 3, JW = 48, JH = 32, DW = 28, DH = 22, MARGIN = 5, WARPS = 8;
+    static constexpr int SEG = 7, NSEG = 3, JW = 48, JH = 32, DW = 28, DH = 22, MARGIN = 5, WARPS = 4, MIN_CTAS = 4;
     static constexpr bool PACKED = false;
 };
 template <> struct LKCfg<31> {
-    static constexpr int SEG = 8, NSEG = 4, JW = 64, JH = 48, DW = 36, DH = 32, MARGIN = 8, WARPS = 4;
+    static constexpr int SEG = 8, NSEG = 4, JW = 64, JH = 48, DW = 36, DH = 32, MARGIN = 8, WARPS = 4, MIN_CTAS = 2;
     static constexpr bool PACKED = true;
 };
 
@@ -330,7 +330,7 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
 }
 
 template <int WIN>
-__global__ void __launch_bounds__(LKCfg<WIN>::WARPS * 32)
+__global__ void __launch_bounds__(LKCfg<WIN>::WARPS * 32, LKCfg<WIN>::MIN_CTAS)
 lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKParams P, SlotList curr, SlotList next,
                 const double *__restrict__ curr_xy, double *__restrict__ next_xy, const int *__restrict__ counts,
                 char *__restrict__ status_out) {
@@ -395,11 +395,11 @@ int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const r
     P.stride = stride;
     if (pyr.win == 21) {
         dim3 grid((stride + LKCfg<21>::WARPS - 1) / LKCfg<21>::WARPS, curr.n);
-        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->stream>>>(maps, P, curr, next, d_curr_xy,
+        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->ls>>>(maps, P, curr, next, d_curr_xy,
                                                                                                       d_next_xy, d_counts, d_status)));
     } else if (pyr.win == 31) {
         dim3 grid((stride + LKCfg<31>::WARPS - 1) / LKCfg<31>::WARPS, curr.n);
-        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->stream>>>(maps, P, curr, next, d_curr_xy,
+        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->ls>>>(maps, P, curr, next, d_curr_xy,
                                                                                                       d_next_xy, d_counts, d_status)));
     } else {
         set_error("LK window %d unsupported (21 or 31)", pyr.win);

@@ -185,7 +185,7 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
         const int tiles_x = (gd.w + 127) / 128, strips = (gd.h + PD_ROWS - 1) / PD_ROWS;
         const int n_items = tiles_x * strips;
         dim3 grid((n_items + PW_WARPS - 1) / PW_WARPS, slots.n);
-        RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(pyr, slots, l, tiles_x, n_items)));
+        RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, l, tiles_x, n_items)));
         ++launches;
     }
     ItemTable tt;
@@ -197,7 +197,7 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
         nt += tt.tiles_x[l] * ((g.h + SC_ROWS - 1) / SC_ROWS);
     }
     tt.first[pyr.nlevels] = nt;
-    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3((nt + PW_WARPS - 1) / PW_WARPS, slots.n), PW_WARPS * 32, 0, ctx->stream>>>(pyr, slots, tt)));
+    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3((nt + PW_WARPS - 1) / PW_WARPS, slots.n), PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, tt)));
     return launches + 1;
 }
 

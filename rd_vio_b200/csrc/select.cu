@@ -40,6 +40,24 @@ __device__ __forceinline__ bool poisson_block_hit(int dcx, int dcy, int span) {
     return dcx == -span && dcy == span + 1;
 }
 
+// true iff no accepted corner lies within minDistance of (x, y): 3x3 cells, 4 in-place slots each
+__device__ __forceinline__ bool grid_pass(const uint4 *cellpts, int gw, int gh, int cell, float md2, int x, int y) {
+    const int xc = x / cell, yc = y / cell;
+    const int x1 = max(xc - 1, 0), y1 = max(yc - 1, 0), x2 = min(xc + 1, gw - 1), y2 = min(yc + 1, gh - 1);
+    bool ok = true;
+    for (int yy = y1; yy <= y2; ++yy)
+        for (int xx = x1; xx <= x2; ++xx) {
+            const uint4 c = cellpts[yy * gw + xx];
+            const unsigned pv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int dx = x - (int)(pv[q] & 0xFFFFu), dy = y - (int)(pv[q] >> 16);
+                if (pv[q] != ~0u && (float)(dx * dx + dy * dy) < md2) ok = false;
+            }
+        }
+    return ok;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, float *__restrict__ gftt_resp,
               int *__restrict__ gftt_counts) {
@@ -49,8 +67,10 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
     float *ax = reinterpret_cast<float *>(hist + 256);                                      // [cap_k]
     float *ay = ax + sp.cap_k;
     float *ar = ay + sp.cap_k;
-    int *anext = reinterpret_cast<int *>(ar + sp.cap_k);
-    int *head = anext + sp.cap_k;                                                           // [gw*gh]
+    // accepted-corner grid: up to 4 corners per cell stored in place as (x | y << 16); a cell of side
+    // round(minDistance) can hold at most 3 points that are pairwise >= minDistance apart.
+    uint4 *cellpts = reinterpret_cast<uint4 *>(smem_raw + (((size_t)SEL_CAP * 8 + 256 * 4 + (size_t)sp.cap_k * 12 + 15) & ~(size_t)15));
+    int *cellcnt = reinterpret_cast<int *>(cellpts + sp.gw * sp.gh);                        // [gw*gh]
 
     __shared__ unsigned s_count, s_nb;
     __shared__ unsigned long long s_prefix, s_hi;
@@ -65,7 +85,7 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
     const unsigned thr_bits = __float_as_uint(thr);       // thr >= 0 here (maxv >= 0)
     const int W = sp.W;
 
-    for (int i = tid; i < sp.gw * sp.gh; i += SEL_THREADS) head[i] = -1;
+    for (int i = tid; i < sp.gw * sp.gh; i += SEL_THREADS) { cellpts[i] = make_uint4(~0u, ~0u, ~0u, ~0u); cellcnt[i] = 0; }
     if (tid == 0) { s_naccepted = 0; s_done = 0; s_hi = ~0ull; }
     __syncthreads();
 
@@ -99,16 +119,7 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
             if (ok && sp.use_min_dist && nacc0 > 0) {
                 const unsigned addr = (unsigned)k;
                 const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
-                const float fx = (float)x, fy = (float)y;
-                const int xc = x / sp.cell, yc = y / sp.cell;
-                const int x1 = max(xc - 1, 0), y1 = max(yc - 1, 0);
-                const int x2 = min(xc + 1, sp.gw - 1), y2 = min(yc + 1, sp.gh - 1);
-                for (int yy = y1; yy <= y2 && ok; ++yy)
-                    for (int xx = x1; xx <= x2 && ok; ++xx)
-                        for (int j = head[yy * sp.gw + xx]; j >= 0; j = anext[j]) {
-                            const float dx = fx - ax[j], dy = fy - ay[j];
-                            if (dx * dx + dy * dy < sp.min_dist2) { ok = false; break; }
-                        }
+                ok = grid_pass(cellpts, sp.gw, sp.gh, sp.cell, sp.min_dist2, x, y);
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (m) {
@@ -138,10 +149,22 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
                 if (tid < 256) hist[tid] = 0;
                 __syncthreads();
                 const unsigned long long prefix = s_prefix;
-                for (unsigned i = tid; i < n; i += SEL_THREADS) {
-                    const unsigned long long k = keys[i];
-                    if ((k & mask) == prefix)
-                        atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+                // Equal digits are the norm in the high passes (responses share their exponent byte): when a whole
+                // warp agrees on the digit one lane adds the count, otherwise plain shared-memory atomics.
+                for (unsigned base = warp * 32; base < n; base += SEL_THREADS) {
+                    const unsigned i = base + lane;
+                    unsigned long long k = 0;
+                    bool part = false;
+                    if (i < n) { k = keys[i]; part = (k & mask) == prefix; }
+                    const unsigned d = (unsigned)(k >> shift) & 255u;
+                    // fast path: every participating lane holds the same digit (typical for the exponent bytes)
+                    const unsigned pm = __ballot_sync(0xffffffffu, part);
+                    if (pm) {
+                        const unsigned d0 = __shfl_sync(0xffffffffu, d, __ffs(pm) - 1);
+                        const bool same = __all_sync(0xffffffffu, !part || d == d0);
+                        if (same) { if (lane == __ffs(pm) - 1) atomicAdd(&hist[d0], (unsigned)__popc(pm)); }
+                        else if (part) atomicAdd(&hist[d], 1u);
+                    }
                 }
                 __syncthreads();
                 if (warp == 0) {
@@ -203,54 +226,119 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
                 __syncthreads();
             }
         }
-        // ---- greedy acceptance (warp 0)
-        if (warp == 0) {
-            int nacc = s_naccepted;
-            for (unsigned base = 0; base < nb && nacc < sp.max_corners; base += 32) {
-                const unsigned idx = base + lane;
-                const bool valid = idx < nb;
-                const unsigned long long k = valid ? batch[idx] : 0ull;
-                const unsigned addr = (unsigned)k;
-                const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
-                const float fx = (float)x, fy = (float)y;
-                bool pass = valid;
-                int xc = 0, yc = 0;
-                if (sp.use_min_dist) {
-                    xc = x / sp.cell; yc = y / sp.cell;
-                    if (pass) {
-                        const int x1 = max(xc - 1, 0), y1 = max(yc - 1, 0);
-                        const int x2 = min(xc + 1, sp.gw - 1), y2 = min(yc + 1, sp.gh - 1);
-                        for (int yy = y1; yy <= y2 && pass; ++yy)
-                            for (int xx = x1; xx <= x2 && pass; ++xx)
-                                for (int j = head[yy * sp.gw + xx]; j >= 0; j = anext[j]) {
-                                    const float dx = fx - ax[j], dy = fy - ay[j];
-                                    if (dx * dx + dy * dy < sp.min_dist2) { pass = false; break; }
-                                }
-                    }
-                }
-                // resolve the sequential dependence inside the chunk
-                unsigned pending = __ballot_sync(0xffffffffu, pass);
-                while (pending && nacc < sp.max_corners) {
-                    const int j = __ffs(pending) - 1;
-                    const float jx = __shfl_sync(0xffffffffu, fx, j), jy = __shfl_sync(0xffffffffu, fy, j);
-                    if (lane == j) {
-                        ax[nacc] = fx; ay[nacc] = fy; ar[nacc] = __uint_as_float((unsigned)(k >> 32));
-                        if (sp.use_min_dist) { anext[nacc] = head[yc * sp.gw + xc]; head[yc * sp.gw + xc] = nacc; }
-                        pass = false;
-                    }
-                    ++nacc;
-                    if (sp.use_min_dist && pass && lane > j) {
-                        const float dx = fx - jx, dy = fy - jy;
-                        if (dx * dx + dy * dy < sp.min_dist2) pass = false;
-                    }
-                    __syncwarp();
-                    pending = __ballot_sync(0xffffffffu, pass) & ~((2u << j) - 1u);
-                }
-                __syncwarp();
+        // ---- greedy acceptance, in rounds.  Round: (1) ALL warps test the not-yet-visited candidates of the
+        // sorted batch against the accepted-corner grid in parallel (a candidate that fails is dead for good:
+        // the accepted set only grows); (2) warp 0 takes the first 32 survivors IN ORDER, resolves the order
+        // dependence among them lane by lane (exactly the sequential greedy) and inserts the winners.
+        // Survivors beyond those 32 are re-tested in the next round against the enlarged grid.
+        {
+            constexpr int NMASK = SEL_CAP / 32;
+            __shared__ unsigned s_mask[NMASK];
+            __shared__ unsigned s_pos;
+            if (tid == 0) s_pos = 0;
+            // alive mask of the batch: a candidate that once failed the grid test is never looked at again
+            for (unsigned wv = tid; wv < NMASK; wv += SEL_THREADS) {
+                const unsigned lo_i = wv * 32u;
+                s_mask[wv] = (lo_i + 32u <= nb) ? ~0u : (lo_i < nb ? ((1u << (nb - lo_i)) - 1u) : 0u);
             }
-            if (lane == 0) {
-                s_naccepted = nacc;
-                s_done = (nacc >= sp.max_corners || n_el <= SEL_CAP) ? 1 : 0;
+            __syncthreads();
+            while (true) {
+                const unsigned pos0 = s_pos;
+                const int nacc_r = s_naccepted;
+                if (pos0 >= nb || nacc_r >= sp.max_corners) break;
+                // (1) re-test the alive, not yet visited candidates against the grown grid
+                for (unsigned wv = (pos0 >> 5) + warp; wv < NMASK; wv += SEL_THREADS / 32) {
+                    const unsigned alive = s_mask[wv];
+                    if (alive == 0u) continue;                                  // warp-uniform
+                    const unsigned idx = wv * 32 + lane;
+                    bool pass = ((alive >> lane) & 1u) && idx >= pos0;
+                    if (pass && sp.use_min_dist && nacc_r > 0) {
+                        const unsigned addr = (unsigned)batch[idx];
+                        const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
+                        pass = grid_pass(cellpts, sp.gw, sp.gh, sp.cell, sp.min_dist2, x, y);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (lane == 0) s_mask[wv] = m;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    // lane r picks the r-th survivor (in batch order)
+                    unsigned c0 = 0, c1 = 0;
+                    // words entirely below pos0 are history; the word containing pos0 was re-masked above (idx >= pos0)
+                    const unsigned w0 = pos0 >> 5;
+                    if (NMASK > 32) {
+                        c0 = ((unsigned)lane >= w0) ? __popc(s_mask[lane]) : 0u;
+                        c1 = ((unsigned)lane + 32u >= w0) ? __popc(s_mask[lane + 32]) : 0u;
+                    } else if (lane < NMASK) c0 = ((unsigned)lane >= w0) ? __popc(s_mask[lane]) : 0u;
+                    unsigned inc0 = c0, inc1 = c1;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned t0 = __shfl_up_sync(0xffffffffu, inc0, d), t1 = __shfl_up_sync(0xffffffffu, inc1, d);
+                        if (lane >= d) { inc0 += t0; inc1 += t1; }
+                    }
+                    const unsigned tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+                    inc1 += tot0;
+                    const unsigned total = __shfl_sync(0xffffffffu, inc1, 31);
+                    const unsigned r = (unsigned)lane;
+                    int widx = -1;
+                    unsigned before = 0;
+                    for (int wq = 0; wq < NMASK; ++wq) {     // warp-uniform shuffles; 64 inclusive counts live across lanes
+                        const unsigned incw = (wq < 32) ? __shfl_sync(0xffffffffu, inc0, wq & 31) : __shfl_sync(0xffffffffu, inc1, wq & 31);
+                        const unsigned cw = (wq < 32) ? __shfl_sync(0xffffffffu, c0, wq & 31) : __shfl_sync(0xffffffffu, c1, wq & 31);
+                        if (widx < 0 && r < total && incw > r) { widx = wq; before = incw - cw; }
+                        if (incw >= 32u) break;               // uniform: the first 32 survivors are located
+                    }
+                    const bool valid = widx >= 0;
+                    unsigned idx = 0;
+                    if (valid) {
+                        unsigned m = s_mask[widx];
+                        for (unsigned t = 0; t < r - before; ++t) m &= m - 1u;      // drop the lower set bits
+                        idx = (unsigned)widx * 32u + (unsigned)(__ffs(m) - 1);
+                    }
+                    const unsigned long long k = valid ? batch[idx] : 0ull;
+                    const unsigned addr = (unsigned)k;
+                    const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
+                    // conflict matrix: bit j of conf = survivor j (higher priority, j < lane) lies within minDistance
+                    unsigned conf = 0;
+                    if (sp.use_min_dist) {
+                        for (int j = 0; j < 31; ++j) {
+                            const int jx = __shfl_sync(0xffffffffu, x, j), jy = __shfl_sync(0xffffffffu, y, j);
+                            const int dx = x - jx, dy = y - jy;
+                            if (j < lane && (float)(dx * dx + dy * dy) < sp.min_dist2) conf |= 1u << j;
+                        }
+                    }
+                    // sequential greedy over the 32 survivors, done with bit operations (every lane redundantly)
+                    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                    unsigned acc = 0;
+                    int room = sp.max_corners - nacc_r;
+                    for (int i = 0; i < 32; ++i) {
+                        const unsigned ci = __shfl_sync(0xffffffffu, conf, i);
+                        if (((vmask >> i) & 1u) && !(ci & acc) && room > 0) { acc |= 1u << i; --room; }
+                    }
+                    // accepted lanes insert themselves (output order = priority order)
+                    if ((acc >> lane) & 1u) {
+                        const int slot = nacc_r + __popc(acc & ((1u << lane) - 1u));
+                        ax[slot] = (float)x; ay[slot] = (float)y; ar[slot] = __uint_as_float((unsigned)(k >> 32));
+                        if (sp.use_min_dist) {
+                            const int cidx = (y / sp.cell) * sp.gw + (x / sp.cell);
+                            const int q = atomicAdd(&cellcnt[cidx], 1);
+                            if (q < 4) reinterpret_cast<unsigned *>(&cellpts[cidx])[q] = (unsigned)x | ((unsigned)y << 16);
+                            else atomicExch(det.overflow, 1u);    // geometrically impossible (<= 3 per cell)
+                        }
+                    }
+                    const int nacc = nacc_r + __popc(acc);
+                    // next round starts after the last survivor taken this round (all of them were decided)
+                    const unsigned taken = min(total, 32u);
+                    const unsigned last_idx = __shfl_sync(0xffffffffu, idx, (int)max(taken, 1u) - 1);
+                    if (lane == 0) {
+                        s_naccepted = nacc;
+                        s_pos = (total <= 32u) ? nb : last_idx + 1;
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                s_done = (s_naccepted >= sp.max_corners || n_el <= SEL_CAP) ? 1 : 0;
                 if (nb) s_hi = batch[nb - 1];
             }
         }
@@ -402,7 +490,7 @@ int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_det
                        float *d_gftt_resp, int *d_gftt_counts) {
     SelectParams sp;
     fill_select_params(ctx, p, 1, sp);
-    const size_t smem = (size_t)SEL_CAP * 8 + 256 * 4 + (size_t)sp.cap_k * 16 + (size_t)sp.gw * sp.gh * 4 + 64;
+    const size_t smem = (size_t)SEL_CAP * 8 + 256 * 4 + (size_t)sp.cap_k * 12 + 16 + (size_t)sp.gw * sp.gh * 20 + 64;
     if (smem > 200 * 1024) {
         set_error("select: shared memory need %zu B exceeds the CTA limit (max_points=%d, grid %dx%d)", smem,
                   p.max_points, sp.gw, sp.gh);
@@ -416,9 +504,8 @@ int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_det
         }
         s_attr = smem;
     }
-    const int pi = (stream == ctx->stream) ? prof_begin(ctx, K_SELECT) : -1;
-    select_kernel<<<n, SEL_THREADS, smem, stream>>>(ctx->det, sp, d_gftt_xy, d_gftt_resp, d_gftt_counts);
-    prof_end(ctx, pi);
+    (void)stream;
+    RDFE_LAUNCH(ctx, K_SELECT, (select_kernel<<<n, SEL_THREADS, smem, ctx->ls>>>(ctx->det, sp, d_gftt_xy, d_gftt_resp, d_gftt_counts)));
     return 1;
 }
 
@@ -436,7 +523,7 @@ int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, con
         }
         s_attr = smem;
     }
-    RDFE_LAUNCH(ctx, K_POISSON, (poisson_append_kernel<<<n, PO_THREADS, smem, ctx->stream>>>(sp, d_gftt_xy, d_gftt_counts, d_xy, d_counts)));
+    RDFE_LAUNCH(ctx, K_POISSON, (poisson_append_kernel<<<n, PO_THREADS, smem, ctx->ls>>>(sp, d_gftt_xy, d_gftt_counts, d_xy, d_counts)));
     return 1;
 }
 
