@@ -313,26 +313,33 @@ def main_b200(args, wl):
         h_status = torch.empty((S, stride), dtype=torch.int8).pin_memory().numpy()
         h_wcnt = np.zeros(S, np.int32)
 
-        def step_host(tt):
+        def submit(tt):
             k = tt % T
             prev, new = slots[tt % 2], slots[(tt + 1) % 2]
-            N.check(L.rdfe_preprocess_batch(h, new.ctypes.data, S, hptrs[(k + 1) % T], W, 6.0, 8, 8), "preprocess")
-            h_next[:] = h_pred[k]
-            N.check(L.rdfe_track_batch(h, prev.ctypes.data, new.ctypes.data, S, C.byref(tp), h_curr[k].ctypes.data,
-                                       h_next.ctypes.data, h_cnt[k].ctypes.data, stride, h_status.ctypes.data), "track")
-            h_wcnt[:] = h_cnt[k]
-            N.check(L.rdfe_detect_batch(h, new.ctypes.data, S, C.byref(dp), h_next.ctypes.data, h_wcnt.ctypes.data, stride,
-                                        None, None, None), "detect")
+            tk = C.c_int()
+            N.check(L.rdfe_frontend_step_submit(h, prev.ctypes.data, new.ctypes.data, S, hptrs[(k + 1) % T], W, 6.0, 8, 8,
+                                                C.byref(tp), h_curr[k].ctypes.data, h_pred[k].ctypes.data,
+                                                h_cnt[k].ctypes.data, C.byref(dp), stride, C.byref(tk)), "step_submit")
+            return tk.value
 
-        h2d = S * H * W + 2 * S * stride * 16 + S * 4 + S * stride * 16 + S * 4
-        d2h = S * stride * 16 + S * stride + S * stride * 16 + S * 4
-        e_steps = max(10, min(args.steps, 100))
-        for _ in range(3):
-            step_host(t); t += 1
+        def wait(tk):
+            N.check(L.rdfe_frontend_step_wait(h, tk, h_next.ctypes.data, h_wcnt.ctypes.data, h_status.ctypes.data), "step_wait")
+
+        h2d = S * H * W + 2 * S * stride * 16 + 2 * S * 4
+        d2h = S * stride * 16 + S * 4 + S * stride + 4
+        e_steps = max(10, min(args.steps, 200))
+        tk = submit(t); t += 1
+        for _ in range(3):                       # warm the pipeline
+            tk2 = submit(t); t += 1
+            wait(tk); tk = tk2
+        wait(tk)
         barrier()
         w0 = time.perf_counter()
-        for _ in range(e_steps):
-            step_host(t); t += 1
+        tk = submit(t); t += 1
+        for _ in range(e_steps - 1):
+            tk2 = submit(t); t += 1
+            wait(tk); tk = tk2
+        wait(tk)
         barrier()
         sec = time.perf_counter() - w0
         sec_t = torch.tensor([sec], dtype=torch.float64, device="cuda")
@@ -340,9 +347,9 @@ def main_b200(args, wl):
             dist.all_reduce(sec_t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * S * e_steps / float(sec_t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "steps": e_steps,
-               "how": "rdfe_preprocess_batch + rdfe_track_batch + rdfe_detect_batch with pinned HOST buffers; every "
-                      "step copies its frames and keypoints H2D and its tracked/detected keypoints + status D2H; wall "
-                      "clock bracketed by barrier+synchronize, max over ranks"}
+               "how": "rdfe_frontend_step_submit/_wait (C ABI, pinned HOST buffers, two steps in flight): every step "
+                      "copies its 64 frames + carried keypoints + predictions H2D and its tracked/detected keypoints, "
+                      "counts and status D2H; wall clock bracketed by barrier+synchronize, max over ranks"}
 
     if rank != 0:
         fe.close()

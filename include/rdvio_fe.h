@@ -158,6 +158,18 @@ RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const 
                            const int *dev_track_counts, char *dev_status, const rdfe_detect_params *dp,
                            int *dev_kp_counts, int stride);
 
+/* Host-buffer form of the same step, pipelined two deep: submit() uploads the frames and keypoints on a copy
+ * stream and enqueues the step; wait() blocks until that step's results are on the host and copies them out.
+ * submit(t+1) may precede wait(t) so that the upload of the next frames overlaps the kernels of the current
+ * step.  next_xy [n][stride][2]: positions of the carried keypoints (prediction where tracking failed) followed
+ * by the newly detected corners, kp_counts[i] entries; status [n][stride].  pred_xy may be NULL (seed with
+ * curr_xy); prev_slots may be NULL (no tracking, counts[i] existing keypoints are taken from curr_xy = NULL -> 0). */
+RDFE_API int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
+                              const uint8_t *const *images, size_t pitch, double clip_limit, int tiles_x, int tiles_y,
+                              const rdfe_track_params *tp, const double *curr_xy, const double *pred_xy, const int *counts,
+                              const rdfe_detect_params *dp, int stride, int *ticket);
+RDFE_API int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy, int *kp_counts, char *status);
+
 /* ---- parity / debugging taps (not on the hot path) ---------------------- */
 /* plane: 0 = 8-bit image (w*h bytes), 1 = Scharr derivative (w*h*2 int16),
  * 2 = image with its win-px REFLECT_101 halo ((w+2win)*(h+2win) bytes). */

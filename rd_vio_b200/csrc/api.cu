@@ -262,6 +262,19 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_clahe_done, cudaEventDisableTiming));
+    for (int p = 0; p < 2; ++p) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_upload[p], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_done[p], cudaEventDisableTiming));
+        CK(cudaMalloc(&ctx->pl_curr[p], npts * 2 * sizeof(double)));
+        CK(cudaMalloc(&ctx->pl_next[p], npts * 2 * sizeof(double)));
+        CK(cudaMalloc(&ctx->pl_counts[p], RDFE_MAX_BATCH * sizeof(int)));
+        CK(cudaMalloc(&ctx->pl_kcounts[p], RDFE_MAX_BATCH * sizeof(int)));
+        CK(cudaMalloc(&ctx->pl_status[p], npts));
+        CK(cudaMalloc(&ctx->pl_ovf[p], sizeof(unsigned)));
+        CK(cudaMallocHost(&ctx->pl_host[p], npts * 17 + RDFE_MAX_BATCH * sizeof(int) + 64));
+    }
     CK(cudaEventCreate(&ctx->ev_t0));
     CK(cudaEventCreate(&ctx->ev_t1));
     ctx->prof_ev = (cudaEvent_t *)calloc(2 * kProfMax, sizeof(cudaEvent_t));
@@ -290,6 +303,15 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_clahe_done) cudaEventDestroy(ctx->ev_clahe_done);
+    for (int p = 0; p < 2; ++p) {
+        if (ctx->ev_upload[p]) cudaEventDestroy(ctx->ev_upload[p]);
+        if (ctx->ev_done[p]) cudaEventDestroy(ctx->ev_done[p]);
+        cudaFree(ctx->pl_curr[p]); cudaFree(ctx->pl_next[p]); cudaFree(ctx->pl_counts[p]); cudaFree(ctx->pl_kcounts[p]);
+        cudaFree(ctx->pl_status[p]); cudaFree(ctx->pl_ovf[p]);
+        if (ctx->pl_host[p]) cudaFreeHost(ctx->pl_host[p]);
+    }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -521,6 +543,7 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     ctx->last_clahe_tiles = tiles_x * tiles_y;
     rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), ctx->d_srcptrs, pitch, vec4, cp), "clahe");
     if (rc) return rc;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_clahe_done, ctx->stream));
     // detection branch (Harris needs only level 0): auxiliary stream, concurrent with pyramid + LK
     const bool ov = ctx->overlap && !ctx->prof_on;
     if (ov) {
@@ -543,6 +566,95 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     }
     if (ov) RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     return check_launch(ctx, launch_poisson_append(ctx, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_counts, dev_next_xy, dev_kp_counts, stride), "poisson");
+}
+
+// ------------------------------------- pipelined host-buffer step (2 stages)
+// submit(t+1) may be called before wait(t): the frames of step t+1 are uploaded on a copy stream while the
+// kernels of step t run; results come back through pinned staging and are handed out by wait().
+int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
+                              const uint8_t *const *images, size_t pitch, double clip_limit, int tiles_x, int tiles_y,
+                              const rdfe_track_params *tp, const double *curr_xy, const double *pred_xy, const int *counts,
+                              const rdfe_detect_params *dp, int stride, int *ticket) {
+    if (!ctx || !new_slots || !images || !counts || !dp || !ticket) { set_error("rdfe_frontend_step_submit: null argument"); return RDFE_ERR_INVALID; }
+    if (n < 1 || n > RDFE_MAX_BATCH || stride < 1 || stride > ctx->cfg.max_points) {
+        set_error("rdfe_frontend_step_submit: n=%d stride=%d out of range (capacity %d)", n, stride, ctx->cfg.max_points);
+        return RDFE_ERR_INVALID;
+    }
+    if (prev_slots && (!tp || !curr_xy)) { set_error("rdfe_frontend_step_submit: tracking needs tp and curr_xy"); return RDFE_ERR_INVALID; }
+    if (pitch < (size_t)ctx->cfg.width) { set_error("rdfe_frontend_step_submit: pitch < width"); return RDFE_ERR_INVALID; }
+    const int p = (int)(ctx->pl_ticket & 1);
+    if (ctx->pl_busy[p]) { set_error("rdfe_frontend_step_submit: stage %d still holds un-waited results (at most 2 steps in flight)", p); return RDFE_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        if (new_slots[i] < 0 || new_slots[i] >= ctx->cfg.num_slots || !ctx->slot_used[new_slots[i]] || !images[i]) {
+            set_error("rdfe_frontend_step_submit: bad slot or image at index %d", i);
+            return RDFE_ERR_INVALID;
+        }
+        if (counts[i] < 0 || counts[i] > stride) { set_error("rdfe_frontend_step_submit: counts[%d]=%d out of range", i, counts[i]); return RDFE_ERR_INVALID; }
+    }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    const size_t xyb = (size_t)n * stride * 2 * sizeof(double);
+    // ---- copy stream: frames into the upload staging of the new slots, keypoints into stage p
+    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_clahe_done, 0));     // last reader of the raw staging
+    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[p], 0));        // stage buffers free again
+    std::vector<const uint8_t *> dptr(n);
+    for (int i = 0; i < n; ++i) {
+        uint8_t *d = ctx->raw + (size_t)new_slots[i] * ctx->raw_slot;
+        if (pitch == ctx->raw_pitch)
+            RDFE_CUDA_OK(cudaMemcpyAsync(d, images[i], pitch * (size_t)ctx->cfg.height, cudaMemcpyHostToDevice, ctx->copy_stream));
+        else
+            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width, (size_t)ctx->cfg.height,
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        dptr[i] = d;
+    }
+    rdfe_track_params tpl;
+    if (tp) tpl = *tp; else rdfe_default_track_params(&tpl);
+    tpl.has_prediction = (prev_slots && pred_xy) ? 1 : 0;
+    if (prev_slots) RDFE_CUDA_OK(cudaMemcpyAsync(ctx->pl_curr[p], curr_xy, xyb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    // detect's existing keypoints = prediction (if any) overwritten by tracked positions, else curr (no tracking: none)
+    if (prev_slots) RDFE_CUDA_OK(cudaMemcpyAsync(ctx->pl_next[p], pred_xy ? pred_xy : curr_xy, xyb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->pl_counts[p], counts, n * sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (prev_slots) RDFE_CUDA_OK(cudaMemcpyAsync(ctx->pl_kcounts[p], counts, n * sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream));
+    else RDFE_CUDA_OK(cudaMemsetAsync(ctx->pl_kcounts[p], 0, n * sizeof(int), ctx->copy_stream));   // first frame: no carried keypoints
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_upload[p], ctx->copy_stream));
+    // ---- main stream: the step, then results into pinned staging
+    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_upload[p], 0));
+    if (prev_slots) RDFE_CUDA_OK(cudaMemsetAsync(ctx->pl_status[p], 0, (size_t)n * stride, ctx->stream));
+    int rc = rdfe_frontend_step_dev(ctx, prev_slots, new_slots, n, dptr.data(), ctx->raw_pitch, clip_limit, tiles_x, tiles_y,
+                                    &tpl, ctx->pl_curr[p], ctx->pl_next[p], ctx->pl_counts[p], ctx->pl_status[p], dp,
+                                    ctx->pl_kcounts[p], stride);
+    if (rc) return rc;
+    uint8_t *hs = ctx->pl_host[p];
+    RDFE_CUDA_OK(cudaMemcpyAsync(hs, ctx->pl_next[p], xyb, cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(hs + xyb, ctx->pl_kcounts[p], n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(hs + xyb + n * sizeof(int), ctx->pl_status[p], (size_t)n * stride, cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(hs + xyb + n * sizeof(int) + (size_t)n * stride, ctx->det.overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_done[p], ctx->stream));
+    ctx->pl_n[p] = n; ctx->pl_stride[p] = stride; ctx->pl_busy[p] = prev_slots ? 2 : 1;
+    *ticket = (int)(ctx->pl_ticket & 0x7fffffff);
+    ctx->pl_ticket++;
+    return RDFE_OK;
+}
+
+int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy, int *kp_counts, char *status) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    const int p = ticket & 1;
+    if (!ctx->pl_busy[p]) { set_error("rdfe_frontend_step_wait: ticket %d has no pending step", ticket); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaEventSynchronize(ctx->ev_done[p]));
+    const int n = ctx->pl_n[p], stride = ctx->pl_stride[p];
+    const size_t xyb = (size_t)n * stride * 2 * sizeof(double);
+    const uint8_t *hs = ctx->pl_host[p];
+    if (next_xy) memcpy(next_xy, hs, xyb);
+    if (kp_counts) memcpy(kp_counts, hs + xyb, n * sizeof(int));
+    if (status && ctx->pl_busy[p] == 2) memcpy(status, hs + xyb + n * sizeof(int), (size_t)n * stride);
+    unsigned ovf;
+    memcpy(&ovf, hs + xyb + n * sizeof(int) + (size_t)n * stride, sizeof ovf);
+    ctx->pl_busy[p] = 0;
+    if (ovf) {
+        cudaMemsetAsync(ctx->det.overflow, 0, sizeof(unsigned), ctx->stream);
+        set_error("corner-candidate buffer overflow (more than %u local maxima in one image)", ctx->det.cand_cap);
+        return RDFE_ERR_OVERFLOW;
+    }
+    return RDFE_OK;
 }
 
 // ------------------------------------------------------------ parity taps

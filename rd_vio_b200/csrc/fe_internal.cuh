@@ -125,6 +125,17 @@ struct rdfe_ctx {
     bool overlap;                 // rdfe_frontend_step*: run Harris + selection on aux_stream beside pyramid + LK
     cudaStream_t aux_stream;      // detection branch of rdfe_frontend_step*
     cudaEvent_t ev_fork, ev_join;
+    // pipelined host-buffer step (rdfe_frontend_step_submit / _wait): two stages
+    cudaStream_t copy_stream;     // H2D of the next step's frames overlaps the current step's kernels
+    cudaEvent_t ev_clahe_done;    // raw upload staging may be overwritten after this
+    cudaEvent_t ev_upload[2], ev_done[2];
+    double *pl_curr[2], *pl_next[2];      // device [RDFE_MAX_BATCH][max_points][2]
+    int *pl_counts[2], *pl_kcounts[2];
+    char *pl_status[2];
+    unsigned *pl_ovf[2];
+    uint8_t *pl_host[2];          // pinned result staging: next_xy | kcounts | status | overflow
+    int pl_n[2], pl_stride[2], pl_busy[2];
+    int64_t pl_ticket;
     cudaEvent_t ev_t0, ev_t1;
     // scratch
     uint8_t *lut;                 // [RDFE_MAX_BATCH][tiles][256]

@@ -246,3 +246,54 @@ def test_fused_step_equals_separate_calls(orc, stream0, frames0):
             assert got_cnt[i] == len(want[i])
             assert np.array_equal(got_xy[i, :got_cnt[i]], want[i])
         fe.close()
+
+
+def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
+    """rdfe_frontend_step_submit/_wait with two steps in flight == the per-call host API."""
+    import ctypes as C
+    from rd_vio_b200 import _native as N
+    from rd_vio_b200.frontend import FrontEnd
+    L = N.lib()
+    n, stride = 2, 300
+    with FrontEnd(752, 480, 3, 21, num_slots=3 * n, max_points=512) as fe:
+        sets = [np.array([fe.acquire() for _ in range(n)], np.int32) for _ in range(3)]
+        fe.preprocess(list(sets[0]), frames0[0:n])
+        kps = fe.detect(list(sets[0]), [np.zeros((0, 2))] * n, 150, 20.0)
+        # expectation: two consecutive steps through the separate host calls
+        want = []
+        carried = kps
+        for stp in range(2):
+            a, b = sets[stp], sets[stp + 1]
+            fe.preprocess(list(b), frames0[stp + 1:stp + 1 + n])
+            nxt, st = fe.track(list(a), list(b), carried, None)
+            merged = []
+            for i in range(n):
+                ex = carried[i].copy()
+                ex[st[i] != 0] = nxt[i][st[i] != 0]
+                merged.append(fe.detect([int(b[i])], [ex], 150, 20.0, stride=stride)[0])
+            want.append((merged, st))
+            carried = [m[:stride] for m in merged]
+        # pipelined: submit step 0 and step 1 back to back (step 1's input = step 0's expected output), then wait
+        imgs = [np.stack(frames0[s + 1:s + 1 + n]) for s in range(2)]
+        tp, dp = fe.track_params(), fe.detect_params(max_points=150, keypoint_distance=20.0)
+        tickets, bufs = [], []
+        inputs = [kps, want[0][0]]
+        for stp in range(2):
+            a, b = sets[stp], sets[stp + 1]
+            curr = np.zeros((n, stride, 2)); cnt = np.zeros(n, np.int32)
+            for i in range(n):
+                c = inputs[stp][i][:stride]
+                curr[i, :len(c)] = c; cnt[i] = len(c)
+            ptrs = (C.c_void_p * n)(*[imgs[stp][i].ctypes.data for i in range(n)])
+            tk = C.c_int()
+            N.check(L.rdfe_frontend_step_submit(fe.handle, a.ctypes.data, b.ctypes.data, n, ptrs, 752, 6.0, 8, 8, C.byref(tp),
+                                                curr.ctypes.data, None, cnt.ctypes.data, C.byref(dp), stride, C.byref(tk)), "submit")
+            tickets.append(tk.value); bufs.append((curr, cnt, ptrs))
+        for stp in range(2):
+            out = np.zeros((n, stride, 2)); oc = np.zeros(n, np.int32); ost = np.zeros((n, stride), np.int8)
+            N.check(L.rdfe_frontend_step_wait(fe.handle, tickets[stp], out.ctypes.data, oc.ctypes.data, ost.ctypes.data), "wait")
+            for i in range(n):
+                m, st = want[stp][0][i], want[stp][1][i]
+                assert oc[i] == len(m), (stp, i, oc[i], len(m))
+                assert np.array_equal(out[i, :oc[i]], m)
+                assert np.array_equal(ost[i, :len(st)], st)
