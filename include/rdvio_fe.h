@@ -158,6 +158,13 @@ RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const 
                            const int *dev_track_counts, char *dev_status, const rdfe_detect_params *dp,
                            int *dev_kp_counts, int stride);
 
+/* Cross-step pipelining for rdfe_frontend_step_dev (off by default).  When on, the preprocess stage of a call
+ * runs on an internal stream and only waits for the step BEFORE the previous one, so it overlaps the previous
+ * step's tracking/detection -- provided its new slots were not touched by the previous step (use three slot
+ * sets in rotation; otherwise the call silently serialises).  Requirement: the source images must already be
+ * complete in device memory when the call is made (they are not ordered against the context stream). */
+RDFE_API int rdfe_set_pipelining(rdfe_ctx *ctx, int on);
+
 /* Host-buffer form of the same step, pipelined two deep: submit() uploads the frames and keypoints on a copy
  * stream and enqueues the step; wait() blocks until that step's results are on the host and copies them out.
  * submit(t+1) may precede wait(t) so that the upload of the next frames overlaps the kernels of the current

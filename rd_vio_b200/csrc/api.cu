@@ -262,6 +262,17 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_apply_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_pre_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_step_done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_step_done[1], cudaEventDisableTiming));
+    CK(cudaMalloc(&ctx->lut2, (size_t)RDFE_MAX_BATCH * kMaxTiles * kMaxTiles * 256));
+    CK(cudaMalloc(&ctx->d_srcptrs2, RDFE_MAX_BATCH * sizeof(uint8_t *)));
+    CK(cudaMalloc(&ctx->d_gftt_xy2, npts * 2 * sizeof(float)));
+    CK(cudaMalloc(&ctx->d_gftt_resp2, npts * sizeof(float)));
+    CK(cudaMalloc(&ctx->d_gftt_counts2, RDFE_MAX_BATCH * sizeof(int)));
+    ctx->last_step_slots = (uint8_t *)calloc((size_t)cfg->num_slots, 1);
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_clahe_done, cudaEventDisableTiming));
     for (int p = 0; p < 2; ++p) {
@@ -304,6 +315,12 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->pre_stream) { cudaStreamSynchronize(ctx->pre_stream); cudaStreamDestroy(ctx->pre_stream); }
+    if (ctx->ev_apply_done) cudaEventDestroy(ctx->ev_apply_done);
+    if (ctx->ev_pre_done) cudaEventDestroy(ctx->ev_pre_done);
+    for (int p = 0; p < 2; ++p) if (ctx->ev_step_done[p]) cudaEventDestroy(ctx->ev_step_done[p]);
+    cudaFree(ctx->lut2); cudaFree(ctx->d_srcptrs2); cudaFree(ctx->d_gftt_xy2); cudaFree(ctx->d_gftt_resp2); cudaFree(ctx->d_gftt_counts2);
+    free(ctx->last_step_slots);
     if (ctx->ev_clahe_done) cudaEventDestroy(ctx->ev_clahe_done);
     for (int p = 0; p < 2; ++p) {
         if (ctx->ev_upload[p]) cudaEventDestroy(ctx->ev_upload[p]);
@@ -332,6 +349,7 @@ int rdfe_sync(rdfe_ctx *ctx) {
     if (!ctx) return RDFE_ERR_INVALID;
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->pre_stream));
     unsigned ovf = 0;
     RDFE_CUDA_OK(cudaMemcpy(&ovf, ctx->det.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
     if (ovf) {
@@ -539,33 +557,72 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         if ((uintptr_t)dev_images[i] % 4) vec4 = 0;
     }
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
-    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, ctx->stream));
+    const bool ov = ctx->overlap && !ctx->prof_on;                 // detection branch beside tracking branch
+    const bool pipe = ov && ctx->pipeline_steps;                   // preprocess of this step beside the previous step
+    const int par = (int)(ctx->step_index & 1);
+    // per-step scratch alternates so that consecutive steps may overlap
+    uint8_t *lut_keep = ctx->lut;
+    const uint8_t **src_keep = ctx->d_srcptrs;
+    float *gxy = par ? ctx->d_gftt_xy2 : ctx->d_gftt_xy, *gre = par ? ctx->d_gftt_resp2 : ctx->d_gftt_resp;
+    int *gcn = par ? ctx->d_gftt_counts2 : ctx->d_gftt_counts;
+    if (par) { ctx->lut = ctx->lut2; ctx->d_srcptrs = ctx->d_srcptrs2; }
+    cudaStream_t ps = pipe ? ctx->pre_stream : ctx->stream;
+    if (pipe) {
+        // the new slots must not be in use by the previous step; then only step s-2 has to be complete
+        bool clash = false;
+        for (int i = 0; i < n; ++i) clash |= ctx->last_step_slots[new_slots[i]] != 0;
+        RDFE_CUDA_OK(cudaStreamWaitEvent(ps, ctx->ev_step_done[clash ? (par ^ 1) : par], 0));
+        if (ctx->images_ready_valid) RDFE_CUDA_OK(cudaStreamWaitEvent(ps, ctx->images_ready, 0));
+    }
+    auto restore = [&]() { ctx->lut = lut_keep; ctx->d_srcptrs = src_keep; ctx->ls = ctx->stream; };
+    // ---- preprocess: CLAHE (level 0 + halo), pyramid, Scharr
+    ctx->ls = ps;
+    cudaError_t ce = cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, ps);
+    if (ce != cudaSuccess) { restore(); set_error("rdfe_frontend_step_dev: %s", cudaGetErrorString(ce)); return RDFE_ERR_CUDA; }
     ctx->last_clahe_tiles = tiles_x * tiles_y;
     rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), ctx->d_srcptrs, pitch, vec4, cp), "clahe");
-    if (rc) return rc;
-    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_clahe_done, ctx->stream));
-    // detection branch (Harris needs only level 0): auxiliary stream, concurrent with pyramid + LK
-    const bool ov = ctx->overlap && !ctx->prof_on;
+    if (rc) { restore(); return rc; }
+    cudaEventRecord(ctx->ev_clahe_done, ps);
+    cudaEventRecord(ctx->ev_apply_done, ps);
+    // ---- detection branch (Harris needs only level 0): auxiliary stream
     if (ov) {
-        RDFE_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_apply_done, 0);
         ctx->ls = ctx->aux_stream;
     }
     rc = check_launch(ctx, launch_harris_candidates(ctx, sn, *dp, nullptr), "harris");
-    if (rc == RDFE_OK)
-        rc = check_launch(ctx, launch_gftt_select(ctx, ctx->ls, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_resp, ctx->d_gftt_counts), "select");
-    ctx->ls = ctx->stream;
-    if (rc) return rc;
-    if (ov) RDFE_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
-    // tracking branch: pyramid levels, Scharr, LK
+    if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, ctx->ls, n, *dp, gxy, gre, gcn), "select");
+    if (rc) { restore(); return rc; }
+    if (ov) cudaEventRecord(ctx->ev_join, ctx->aux_stream);
+    // ---- tracking branch: pyramid levels + Scharr (still on the preprocess stream), then LK on the main stream
+    ctx->ls = ps;
     rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
-    if (rc) return rc;
+    if (rc) { restore(); return rc; }
+    if (pipe) {
+        cudaEventRecord(ctx->ev_pre_done, ps);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_pre_done, 0);
+    }
+    restore();
     if (prev_slots) {
         rc = check_launch(ctx, launch_lk(ctx, spv, sn, *tp, dev_curr_xy, dev_next_xy, dev_track_counts, stride, dev_status), "lk");
         if (rc) return rc;
     }
     if (ov) RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    return check_launch(ctx, launch_poisson_append(ctx, n, *dp, ctx->d_gftt_xy, ctx->d_gftt_counts, dev_next_xy, dev_kp_counts, stride), "poisson");
+    rc = check_launch(ctx, launch_poisson_append(ctx, n, *dp, gxy, gcn, dev_next_xy, dev_kp_counts, stride), "poisson");
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_step_done[par], ctx->stream));
+    memset(ctx->last_step_slots, 0, (size_t)ctx->cfg.num_slots);
+    for (int i = 0; i < n; ++i) { ctx->last_step_slots[new_slots[i]] = 1; if (prev_slots) ctx->last_step_slots[prev_slots[i]] = 1; }
+    ctx->step_index++;
+    return RDFE_OK;
+}
+
+int rdfe_set_pipelining(rdfe_ctx *ctx, int on) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->pre_stream));
+    ctx->pipeline_steps = on != 0;
+    return RDFE_OK;
 }
 
 // ------------------------------------- pipelined host-buffer step (2 stages)
@@ -619,9 +676,12 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
     // ---- main stream: the step, then results into pinned staging
     RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_upload[p], 0));
     if (prev_slots) RDFE_CUDA_OK(cudaMemsetAsync(ctx->pl_status[p], 0, (size_t)n * stride, ctx->stream));
+    ctx->images_ready = ctx->ev_upload[p];        // the preprocess stream (if pipelining) must see the uploads too
+    ctx->images_ready_valid = true;
     int rc = rdfe_frontend_step_dev(ctx, prev_slots, new_slots, n, dptr.data(), ctx->raw_pitch, clip_limit, tiles_x, tiles_y,
                                     &tpl, ctx->pl_curr[p], ctx->pl_next[p], ctx->pl_counts[p], ctx->pl_status[p], dp,
                                     ctx->pl_kcounts[p], stride);
+    ctx->images_ready_valid = false;
     if (rc) return rc;
     uint8_t *hs = ctx->pl_host[p];
     RDFE_CUDA_OK(cudaMemcpyAsync(hs, ctx->pl_next[p], xyb, cudaMemcpyDeviceToHost, ctx->stream));

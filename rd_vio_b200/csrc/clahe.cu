@@ -145,28 +145,32 @@ clahe_apply_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int src
         const uint8_t *srow = img + (size_t)y * pitch;
         for (int g = lane; g < groups; g += 32) {
             const int x = g << 2;
-            const int nvalid = min(4, cp.W - x);
             unsigned px;
-            if (src_vec4 && nvalid == 4) {
+            if (src_vec4 && x + 4 <= cp.W) {
                 px = __ldg(reinterpret_cast<const unsigned *>(srow + x));
             } else {
                 px = 0;
-                for (int i = 0; i < nvalid; ++i) px |= (unsigned)__ldg(srow + x + i) << (8 * i);
+                for (int i = 0; i < min(4, cp.W - x); ++i) px |= (unsigned)__ldg(srow + x + i) << (8 * i);
             }
             const float4 xa4 = *reinterpret_cast<const float4 *>(xa_s + x);
             const uint4 cb4 = *reinterpret_cast<const uint4 *>(cb_s + x);
             const float xas[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
             const unsigned cbs[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
-            unsigned out = 0;
+            unsigned rb[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float xa = xas[i], xa1 = 1.0f - xa;
-                const unsigned e = comb[cbs[i] + ((px >> (8 * i)) & 255u)];
-                const float l11 = u8_to_float(e & 255u), l12 = u8_to_float((e >> 8) & 255u);
-                const float l21 = u8_to_float((e >> 16) & 255u), l22 = u8_to_float(e >> 24);
+                const unsigned e = comb[cbs[i] + __byte_perm(px, 0u, 0x4440u | (unsigned)i)];
+                // four LUT bytes -> floats: PRMT builds the bits of 2^23 + b, one FADD removes the 2^23 (exact)
+                const float l11 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7650u)) - 8388608.0f;
+                const float l12 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7651u)) - 8388608.0f;
+                const float l21 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7652u)) - 8388608.0f;
+                const float l22 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7653u)) - 8388608.0f;
                 const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
-                out |= float_to_u8_rn(res) << (8 * i);
+                // res in [0, 255.5): adding 1.5 * 2^23 leaves rint(res) (ties to even) in the low mantissa byte
+                rb[i] = __float_as_uint(res + 12582912.0f);
             }
+            const unsigned out = __byte_perm(__byte_perm(rb[0], rb[1], 0x0040u), __byte_perm(rb[2], rb[3], 0x0040u), 0x5410u);
             store4_with_halo(dst, dpitch, cp.W, cp.H, pyr.win, x, y, out);
         }
     }

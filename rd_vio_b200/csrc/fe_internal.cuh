@@ -71,13 +71,21 @@ __device__ __forceinline__ void store4_row(uint8_t *r, int W, int win, int x, in
         }
     }
 }
-__device__ __forceinline__ void store4_with_halo(uint8_t *org, int pitch, int W, int H, int win, int x, int y,
-                                                 unsigned v4) {
+// border groups only (about 15 % of level 0)
+__device__ __forceinline__ void store4_border(uint8_t *org, int pitch, int W, int H, int win, int x, int y, unsigned v4) {
     const int nvalid = min(4, W - x);
     const bool near_x = (x <= win) || (x + 3 >= W - 1 - win);
     store4_row(org + (ptrdiff_t)y * pitch, W, win, x, nvalid, v4, near_x);
     if (y >= 1 && y <= win) store4_row(org - (ptrdiff_t)y * pitch, W, win, x, nvalid, v4, near_x);
     if (y >= H - 1 - win && y <= H - 2) store4_row(org + (ptrdiff_t)(2 * (H - 1) - y) * pitch, W, win, x, nvalid, v4, near_x);
+}
+__device__ __forceinline__ void store4_with_halo(uint8_t *org, int pitch, int W, int H, int win, int x, int y,
+                                                 unsigned v4) {
+    // interior: no mirror image of these pixels lies in the halo (small levels may have no interior at all)
+    if (x > win && x + 3 < W - 1 - win && y > win && y < H - 1 - win)
+        *reinterpret_cast<unsigned *>(org + (ptrdiff_t)y * pitch + x) = v4;
+    else
+        store4_border(org, pitch, W, H, win, x, y, v4);
 }
 #endif
 
@@ -125,6 +133,18 @@ struct rdfe_ctx {
     bool overlap;                 // rdfe_frontend_step*: run Harris + selection on aux_stream beside pyramid + LK
     cudaStream_t aux_stream;      // detection branch of rdfe_frontend_step*
     cudaEvent_t ev_fork, ev_join;
+    // cross-step pipelining (rdfe_set_pipelining): preprocess of step s+1 on pre_stream beside track/detect of step s
+    bool pipeline_steps;
+    cudaStream_t pre_stream;
+    cudaEvent_t ev_apply_done, ev_pre_done, ev_step_done[2];
+    int64_t step_index;
+    uint8_t *last_step_slots;     // [num_slots] 1 = touched by the previous step
+    uint8_t *lut2;                // second CLAHE LUT buffer (steps alternate)
+    const uint8_t **d_srcptrs2;
+    float *d_gftt_xy2, *d_gftt_resp2;
+    int *d_gftt_counts2;
+    cudaEvent_t images_ready;     // optional: event the source images depend on (set by the host pipeline)
+    bool images_ready_valid;
     // pipelined host-buffer step (rdfe_frontend_step_submit / _wait): two stages
     cudaStream_t copy_stream;     // H2D of the next step's frames overlaps the current step's kernels
     cudaEvent_t ev_clahe_done;    // raw upload staging may be overwritten after this

@@ -297,3 +297,50 @@ def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
                 assert oc[i] == len(m), (stp, i, oc[i], len(m))
                 assert np.array_equal(out[i, :oc[i]], m)
                 assert np.array_equal(ost[i, :len(st)], st)
+
+
+def test_cross_step_pipelining_equals_serial(stream0, frames0):
+    """rdfe_set_pipelining(1) with three slot sets: preprocess of step t+1 overlaps step t; results must equal
+    the serial schedule bit for bit."""
+    import ctypes as C
+    import torch
+    from rd_vio_b200 import _native as N
+    from rd_vio_b200.frontend import FrontEnd
+    L = N.lib()
+    n, stride, steps = 4, 300, 5
+    ts = torch.cuda.Stream()
+    results = {}
+    with torch.cuda.stream(ts):
+        for mode in (0, 1):
+            fe = FrontEnd(752, 480, 3, 21, num_slots=3 * n, max_points=512, stream=ts.cuda_stream)
+            N.check(L.rdfe_set_pipelining(fe.handle, mode), "set_pipelining")
+            sets = [np.array([fe.acquire() for _ in range(n)], np.int32) for _ in range(3)]
+            imgs = torch.from_numpy(np.stack([np.stack([frames0[(s + i) % 6] for i in range(n)]) for s in range(steps + 1)])).cuda()
+            fe.preprocess(list(sets[0]), [frames0[i % 6] for i in range(n)])
+            kps = fe.detect(list(sets[0]), [np.zeros((0, 2))] * n, 150, 20.0)
+            curr = torch.zeros((n, stride, 2), dtype=torch.float64)
+            cnt = torch.zeros(n, dtype=torch.int32)
+            for i in range(n):
+                curr[i, :len(kps[i])] = torch.from_numpy(kps[i]); cnt[i] = len(kps[i])
+            curr, cnt = curr.cuda(), cnt.cuda()
+            tp, dp = fe.track_params(has_prediction=0), fe.detect_params(max_points=150, keypoint_distance=20.0)
+            outs = []
+            for s in range(steps):          # all steps are enqueued back to back: no host sync in between
+                work = curr.clone(); kcnt = cnt.clone()
+                status = torch.zeros((n, stride), dtype=torch.int8, device="cuda")
+                ptrs = (C.c_void_p * n)(*[imgs[s + 1, i].data_ptr() for i in range(n)])
+                prev, new = sets[s % 3], sets[(s + 1) % 3]
+                N.check(L.rdfe_frontend_step_dev(fe.handle, prev.ctypes.data, new.ctypes.data, n, ptrs, 752, 6.0, 8, 8, C.byref(tp),
+                                                 C.c_void_p(curr.data_ptr()), C.c_void_p(work.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                                 C.c_void_p(status.data_ptr()), C.byref(dp), C.c_void_p(kcnt.data_ptr()), stride), "step")
+                outs.append((work, kcnt, status, ptrs))
+                curr, cnt = work, torch.clamp(kcnt, max=stride)     # next step tracks everything detected so far
+            fe.sync()
+            results[mode] = [(w.cpu().numpy(), k.cpu().numpy(), st.cpu().numpy()) for w, k, st, _ in outs]
+            fe.close()
+    for s in range(steps):
+        a, b = results[0][s], results[1][s]
+        assert np.array_equal(a[1], b[1]), f"step {s}: counts differ"
+        assert np.array_equal(a[2], b[2]), f"step {s}: status differs"
+        for i in range(n):
+            assert np.array_equal(a[0][i, :a[1][i]], b[0][i, :b[1][i]]), f"step {s} image {i}"
