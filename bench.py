@@ -178,7 +178,18 @@ def main_b200(args, wl):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL only reduces timing scalars here (streams share no state).  Its start-up banner goes to stdout,
+        # which must carry exactly one JSON line: point fd 1 at stderr while the communicator comes up.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from rd_vio_b200 import _native as N
     from rd_vio_b200.frontend import FrontEnd
     from rd_vio_b200.synthetic import SyntheticStream

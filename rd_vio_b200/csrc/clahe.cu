@@ -21,7 +21,7 @@ namespace rdfe {
 constexpr int kHistWarps = 8;
 
 __global__ void __launch_bounds__(kHistWarps * 32)
-clahe_hist_lut_kernel(const uint8_t *const *__restrict__ src, size_t pitch, ClaheParams cp,
+clahe_hist_lut_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int vec4, ClaheParams cp,
                       uint8_t *__restrict__ lut) {
     __shared__ unsigned hist[kHistWarps][256];
     __shared__ unsigned wsum[kHistWarps];
@@ -34,7 +34,34 @@ clahe_hist_lut_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Clah
     __syncthreads();
 
     const int x0 = tx * cp.tw, y0 = ty * cp.th;
-    if (!cp.padded) {
+    if (!cp.padded && vec4) {
+        // aligned 32-bit words covering the tile row; bytes outside [x0, x0+tw) are masked.  All the row
+        // loads of a warp are issued before the first atomic so that they overlap (the kernel is latency-bound).
+        const int wa = x0 & ~3;                                    // first aligned column
+        const int nwords = ((x0 + cp.tw + 3) & ~3) - wa >> 2;     // words per row
+        constexpr int RPW = 8;                                     // rows per warp batch
+        for (int yb = warp * RPW; yb < cp.th; yb += kHistWarps * RPW) {
+            for (int wi = lane; wi < nwords; wi += 32) {
+                unsigned wv[RPW];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const int y = yb + r;
+                    wv[r] = (y < cp.th) ? __ldg(reinterpret_cast<const unsigned *>(img + (size_t)(y0 + y) * pitch + wa) + wi) : 0u;
+                }
+                const int xw = wa + 4 * wi;
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    if (yb + r < cp.th) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int x = xw + k;
+                            if (x >= x0 && x < x0 + cp.tw) atomicAdd(&hist[warp][(wv[r] >> (8 * k)) & 255u], 1u);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (!cp.padded) {
         for (int y = warp; y < cp.th; y += kHistWarps) {
             const uint8_t *row = img + (size_t)(y0 + y) * pitch + x0;
             for (int x = lane; x < cp.tw; x += 32) atomicAdd(&hist[warp][__ldg(row + x)], 1u);
@@ -180,7 +207,7 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
                  int src_vec4, const ClaheParams &cp) {
     const int ntiles = cp.tiles_x * cp.tiles_y;
     dim3 g1(ntiles, slots.n);
-    RDFE_LAUNCH(ctx, K_CLAHE_HIST, (clahe_hist_lut_kernel<<<g1, kHistWarps * 32, 0, ctx->ls>>>(d_src, src_pitch, cp, ctx->lut)));
+    RDFE_LAUNCH(ctx, K_CLAHE_HIST, (clahe_hist_lut_kernel<<<g1, kHistWarps * 32, 0, ctx->ls>>>(d_src, src_pitch, src_vec4, cp, ctx->lut)));
 
     // row bands: split every interpolation cell row into chunks of <= RB rows
     ApplyBands bands;

@@ -58,7 +58,7 @@ __device__ __forceinline__ double shfl_down_d(double v) {
 }
 
 template <bool kFma>
-__global__ void __launch_bounds__(HW_WARPS * 32, 4)
+__global__ void __launch_bounds__(HW_WARPS * 32)
 harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
                   int n_items) {
     __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];

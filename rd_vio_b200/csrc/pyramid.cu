@@ -105,47 +105,46 @@ struct ItemTable {
 __global__ void __launch_bounds__(PW_WARPS * 32)
 scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item_g = blockIdx.x * PW_WARPS + warp;
-    if (item_g >= tt.first[pyr.nlevels]) return;
-    int l = 0;
-    while (l + 1 < pyr.nlevels && item_g >= tt.first[l + 1]) ++l;
-    const int item = item_g - tt.first[l];
+    const int l = blockIdx.z;                                // level
+    const int item = blockIdx.x * PW_WARPS + warp;
+    if (item >= tt.first[l]) return;                         // tt.first[l] = work items of this level
     const int slot = slots.v[blockIdx.y];
-    const LevelGeom g = pyr.lv[l];
-    const uint8_t *src = pyr.image_origin(l, slot);
-    uint8_t *dst = reinterpret_cast<uint8_t *>(pyr.deriv_origin(l, slot));
-    const int c0 = (item % tt.tiles_x[l]) * 128 + 4 * lane;
-    const int y0 = (item / tt.tiles_x[l]) * SC_ROWS;
-    const int rows = min(SC_ROWS, g.h - y0);
-    const bool active = c0 < g.w;
-    const bool ld_ok = (c0 + 3 <= g.w + pyr.win - 1);        // inside the halo (also the first inactive lane)
-    const bool edge_l = (lane == 0), edge_r = (lane == 31);
+    // level geometry into registers once (the loop below only bumps pointers)
+    const int gw = pyr.lv[l].w, gh = pyr.lv[l].h, ipitch = pyr.lv[l].ipitch, dpitch = pyr.lv[l].dpitch;
+    const int tiles_x = tt.tiles_x[l];
+    const int c0 = (item % tiles_x) * 128 + 4 * lane;
+    const int y0 = (item / tiles_x) * SC_ROWS;
+    const int rows = min(SC_ROWS, gh - y0);
+    const bool active = c0 < gw;
+    const bool ld_ok = (c0 + 3 <= gw + pyr.win - 1);          // inside the halo (also the first inactive lane)
+    const bool el = (lane == 0) && active, er = (lane == 31) && active;
+    const bool full = active && (c0 + 3 < gw);
+    const uint8_t *rp = pyr.image_origin(l, slot) + (ptrdiff_t)(y0 - 1) * ipitch + c0;     // row y0-1
+    uint8_t *op = reinterpret_cast<uint8_t *>(pyr.deriv_origin(l, slot)) + (size_t)y0 * dpitch + 4 * (size_t)c0;
 
-    int d1A[4], d1B[4], s2A[4], s2B[4];                      // rows y-2, y-1: p(x+1)-p(x-1) and 3p(x-1)+10p(x)+3p(x+1)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) d1A[k] = d1B[k] = s2A[k] = s2B[k] = 0;
-
-    const bool el = edge_l && active, er = edge_r && active;
-    auto load_row = [&](int y, unsigned &w, unsigned &xl, unsigned &xr) {
-        const uint8_t *row = src + (ptrdiff_t)y * g.ipitch;
-        w = 0u; xl = 0u; xr = 0u;
-        if (ld_ok) w = *reinterpret_cast<const unsigned *>(row + c0);
-        if (el) xl = *reinterpret_cast<const unsigned *>(row + c0 - 4);
-        if (er) xr = *reinterpret_cast<const unsigned *>(row + c0 + 4);
-    };
-    unsigned wn, xln, xrn;
-    load_row(y0 - 1, wn, xln, xrn);
-    for (int s = 0; s < rows + 2; ++s) {
-        const int y = y0 - 1 + s;
+    // rows y-2, y-1: p(x+1)-p(x-1) and 3p(x-1)+10p(x)+3p(x+1)
+    int d1A[4] = {0, 0, 0, 0}, d1B[4] = {0, 0, 0, 0}, s2A[4] = {0, 0, 0, 0}, s2B[4] = {0, 0, 0, 0};
+    unsigned wn = 0, xln = 0, xrn = 0;
+    if (ld_ok) wn = *reinterpret_cast<const unsigned *>(rp);
+    if (el) xln = *reinterpret_cast<const unsigned *>(rp - 4);
+    if (er) xrn = *reinterpret_cast<const unsigned *>(rp + 4);
+    const int nsteps = rows + 2;
+#pragma unroll 3
+    for (int s = 0; s < nsteps; ++s) {
         const unsigned w = wn, xl = xln, xr = xrn;
-        if (s + 1 < rows + 2) load_row(y + 1, wn, xln, xrn);
+        rp += ipitch;
+        if (s + 1 < nsteps) {                                 // software pipelining: next row in flight
+            if (ld_ok) wn = *reinterpret_cast<const unsigned *>(rp);
+            if (el) xln = *reinterpret_cast<const unsigned *>(rp - 4);
+            if (er) xrn = *reinterpret_cast<const unsigned *>(rp + 4);
+        }
         unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
         if (el) wl = xl;
         if (er) wr = xr;
         int p[6];
-        p[0] = (int)bfe8(wl, 3);
-        p[1] = (int)bfe8(w, 0); p[2] = (int)bfe8(w, 1); p[3] = (int)bfe8(w, 2); p[4] = (int)bfe8(w, 3);
-        p[5] = (int)bfe8(wr, 0);
+        p[0] = (int)(wl >> 24);
+        p[1] = (int)(w & 0xFFu); p[2] = (int)__byte_perm(w, 0u, 0x4441u); p[3] = (int)__byte_perm(w, 0u, 0x4442u); p[4] = (int)(w >> 24);
+        p[5] = (int)(wr & 0xFFu);
         int d1N[4], s2N[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -153,24 +152,21 @@ scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
             s2N[k] = 3 * (p[k] + p[k + 2]) + 10 * p[k + 1];
         }
         if (s >= 2) {
-            const int r = y - 1;                              // centre row
             unsigned o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int gx = 3 * (d1A[k] + d1N[k]) + 10 * d1B[k];
                 const int gy = s2N[k] - s2A[k];
-                o[k] = ((unsigned)gx & 0xFFFFu) | ((unsigned)gy << 16);
+                o[k] = __byte_perm((unsigned)gx, (unsigned)gy, 0x5410u);      // (dx, dy) int16 pair
             }
-            if (active) {
-                uint8_t *out = dst + (size_t)r * g.dpitch + 4 * (size_t)c0;
-                if (c0 + 3 < g.w) {
-                    *reinterpret_cast<uint4 *>(out) = make_uint4(o[0], o[1], o[2], o[3]);
-                } else {
+            if (full) {
+                *reinterpret_cast<uint4 *>(op) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else if (active) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (c0 + k < g.w) reinterpret_cast<unsigned *>(out)[k] = o[k];
-                }
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + k < gw) reinterpret_cast<unsigned *>(op)[k] = o[k];
             }
+            op += dpitch;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) { d1A[k] = d1B[k]; d1B[k] = d1N[k]; s2A[k] = s2B[k]; s2B[k] = s2N[k]; }
@@ -189,15 +185,14 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
         ++launches;
     }
     ItemTable tt;
-    int nt = 0;
+    int max_items = 0;
     for (int l = 0; l < pyr.nlevels; ++l) {
         const LevelGeom &g = pyr.lv[l];
-        tt.first[l] = nt;
         tt.tiles_x[l] = (g.w + 127) / 128;
-        nt += tt.tiles_x[l] * ((g.h + SC_ROWS - 1) / SC_ROWS);
+        tt.first[l] = tt.tiles_x[l] * ((g.h + SC_ROWS - 1) / SC_ROWS);      // work items (warps) of level l
+        max_items = tt.first[l] > max_items ? tt.first[l] : max_items;
     }
-    tt.first[pyr.nlevels] = nt;
-    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3((nt + PW_WARPS - 1) / PW_WARPS, slots.n), PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, tt)));
+    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3((max_items + PW_WARPS - 1) / PW_WARPS, slots.n, pyr.nlevels), PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, tt)));
     return launches + 1;
 }
 
