@@ -34,7 +34,7 @@ namespace rdfe {
 constexpr int HR_ROWS = 44;            // output rows per warp strip
 constexpr int HR_COLS = 120;           // output columns per warp (lanes 1..30)
 constexpr int HW_WARPS = 4;            // warps per CTA
-constexpr int HW_BUF = 128;            // per-warp candidate staging (keys)
+constexpr int HW_BUF = 256;            // per-warp candidate staging (keys)
 
 __device__ __forceinline__ float byte_f(unsigned w, int k) {
     // byte k of w as float: build 2^23 + b by PRMT, subtract 2^23 (exact)
@@ -57,67 +57,69 @@ __device__ __forceinline__ double shfl_down_d(double v) {
     return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), 1), __shfl_down_sync(0xffffffffu, __double2loint(v), 1));
 }
 
-template <bool kFma>
-__global__ void __launch_bounds__(HW_WARPS * 32)
-harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
-                  int n_items) {
-    __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * HW_WARPS + warp;
-    if (item >= n_items) return;
-    const int b = blockIdx.y, slot = slots.v[b];
-    const LevelGeom g = pyr.lv[0];
-    const int W = g.w, H = g.h;
-    const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * HR_ROWS;
+// One strip (HR_ROWS x 120 outputs) by one warp.  BORDER = false is the lean variant for strips whose
+// whole 128-column x (rows+6)-row footprint lies inside the image: no mirror/sign/validity logic at all.
+template <bool kFma, bool BORDER>
+__device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0, float k,
+                                             const DetectScratch &det, int b, float *__restrict__ response,
+                                             unsigned long long *buf, unsigned *cnt) {
+    const int lane = threadIdx.x & 31;
     const int c0 = x0 - 4 + 4 * lane;                       // first of this lane's 4 columns
-    const uint8_t *org = pyr.image_origin(0, slot);
-    const bool ld_ok = (c0 + 3 <= W + 20) && (c0 >= -20);   // inside the materialised halo
+    const bool ld_ok = BORDER ? ((c0 + 3 <= W + 20) && (c0 >= -20)) : true;   // inside the materialised halo
+    const bool out_lane = lane >= 1 && lane <= 30;          // lanes 0 and 31 are apron
     const double sc = 1.0 / (4.0 * 3.0 * 255.0);
     const float k0 = (float)sc, k1 = (float)(2.0 * sc);
-    // per-column flags
-    bool mir[4], bflipx[4], cvalid[4];
+    // per-column flags (BORDER only)
+    bool mir[4], bflipx[4];
+    float cinv[4], cemit[4];                                // 0 or -inf: column outside the image / not emittable
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int x = c0 + i;
-        mir[i] = (x == -1) || (x == W);
-        bflipx[i] = (x < 0) || (x >= W);
-        cvalid[i] = (x >= 0) && (x < W);
+        mir[i] = BORDER && ((x == -1) || (x == W));
+        bflipx[i] = BORDER && ((x < 0) || (x >= W));
+        cinv[i] = (BORDER && (x < 0 || x >= W)) ? -INFINITY : 0.0f;
+        cemit[i] = (!out_lane || (BORDER && (x < 1 || x >= W - 1))) ? -INFINITY : 0.0f;
     }
     float dA[4] = {0, 0, 0, 0}, dB[4] = {0, 0, 0, 0};       // d(y-2), d(y-1)
     float sA[4] = {0, 0, 0, 0}, sB[4] = {0, 0, 0, 0};       // s(y-2), s(y-1)
     double pa[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0}, pc[4] = {0, 0, 0, 0};   // products of row p-1
     double ta[4] = {0, 0, 0, 0}, tb[4] = {0, 0, 0, 0}, tc[4] = {0, 0, 0, 0};   // a(p-2)+a(p-1)
-    float Rm[6], Rc[6];                                      // responses of rows q-2 (hmax3 in [1..4]) and q-1 (cols -1..4)
+    float Rm[6], Rc[6];                                      // rows q-2 (hmax3 in [1..4]) and q-1 (cols -1..4)
 #pragma unroll
     for (int i = 0; i < 6; ++i) { Rm[i] = -INFINITY; Rc[i] = -INFINITY; }
     float tmax = 0.0f;
-    int nbuf = 0;                                            // warp-uniform count of staged keys
-    unsigned long long *buf = s_buf[warp];
 
     auto flush = [&]() {
+        const unsigned nb = *cnt;
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&det.cand_count[b], (unsigned)nbuf);
+        if (lane == 0) base = atomicAdd(&det.cand_count[b], nb);
         base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane; i < nbuf; i += 32) {
+        for (unsigned i = lane; i < nb; i += 32) {
             const unsigned pos = base + i;
             if (pos < det.cand_cap) det.cand[(size_t)b * det.cand_cap + pos] = buf[i];
             else atomicExch(det.overflow, 1u);
         }
         __syncwarp();
-        nbuf = 0;
+        if (lane == 0) *cnt = 0u;
+        __syncwarp();
     };
 
-    const int steps = min(HR_ROWS, H - y0) + 6;
+    const int rows = min(HR_ROWS, H - y0);
+    const int steps = rows + 6;
     // software pipelining: the pixel words of rows j+1, j+2 are in flight while row j is processed
-    const uint8_t *rowp = org + (ptrdiff_t)(y0 - 3) * g.ipitch + c0;
+    const uint8_t *rowp = org + (ptrdiff_t)(y0 - 3) * ipitch + c0;
     unsigned wq0 = 0, wq1 = 0;
-    if (ld_ok) { wq0 = *reinterpret_cast<const unsigned *>(rowp); wq1 = *reinterpret_cast<const unsigned *>(rowp + g.ipitch); }
+    if (ld_ok) { wq0 = *reinterpret_cast<const unsigned *>(rowp); wq1 = *reinterpret_cast<const unsigned *>(rowp + ipitch); }
+    rowp += 2 * (ptrdiff_t)ipitch;
+    float *resp_row = response ? response + ((size_t)b * H + (y0 - 5)) * W + c0 : nullptr;   // row q = y0-5+j
+    unsigned addr_row = (unsigned)((y0 - 6) * W + c0);       // pixel address of (row n = y0-6+j, column c0)
+#pragma unroll 2
     for (int j = 0; j < steps; ++j) {
-        const int y = y0 - 3 + j;                            // pixel row consumed this step (>= -3, <= H+2)
-        // ---- pixels c0-1 .. c0+4 as floats
+        // ---- pixels c0-1 .. c0+4 of row y = y0-3+j as floats
         const unsigned w = wq0;
         wq0 = wq1;
-        if (ld_ok && j + 2 < steps) wq1 = *reinterpret_cast<const unsigned *>(rowp + (ptrdiff_t)(j + 2) * g.ipitch);
+        if (ld_ok && j + 2 < steps) wq1 = *reinterpret_cast<const unsigned *>(rowp);
+        rowp += ipitch;
         const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
         float p[6];
         p[0] = byte_f(wl, 3);
@@ -132,15 +134,15 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
             dN[i] = p[i + 2] - p[i];
             if (!kFma) {
                 const float k1p = k1 * p[i + 1];
-                sN[i] = mir[i] ? ((k0p[i + 2] + k1p) + k0p[i]) : ((k0p[i] + k1p) + k0p[i + 2]);
+                sN[i] = (BORDER && mir[i]) ? ((k0p[i + 2] + k1p) + k0p[i]) : ((k0p[i] + k1p) + k0p[i + 2]);
             } else {
-                sN[i] = mir[i] ? __fmaf_rn(k0, p[i], __fmaf_rn(k1, p[i + 1], k0p[i + 2]))
-                               : __fmaf_rn(k0, p[i + 2], __fmaf_rn(k1, p[i + 1], k0p[i]));
+                sN[i] = (BORDER && mir[i]) ? __fmaf_rn(k0, p[i], __fmaf_rn(k1, p[i + 1], k0p[i + 2]))
+                                           : __fmaf_rn(k0, p[i + 2], __fmaf_rn(k1, p[i + 1], k0p[i]));
             }
         }
         // ---- gradient products of row pr = y-1 (needs rows y-2, y-1, y)
-        const int pr = y - 1;
-        const bool bflipy = (pr < 0) || (pr >= H);
+        const int pr = y0 - 4 + j;
+        const bool bflipy = BORDER && ((pr < 0) || (pr >= H));
         double na[4], nb[4], nc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -149,7 +151,7 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
             else gx = __fmaf_rn(k0, dA[i] + dN[i], k1 * dB[i]);
             const float gy = sN[i] - sA[i];
             float fb = gx * gy;
-            if (bflipx[i] != bflipy) fb = -fb;
+            if (BORDER && (bflipx[i] != bflipy)) fb = -fb;
             na[i] = (double)(gx * gx);
             nb[i] = (double)fb;
             nc[i] = (double)(gy * gy);
@@ -165,7 +167,7 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
         }
         va[0] = shfl_up_d(va[4]); vb[0] = shfl_up_d(vb[4]); vc[0] = shfl_up_d(vc[4]);
         va[5] = shfl_down_d(va[1]); vb[5] = shfl_down_d(vb[1]); vc[5] = shfl_down_d(vc[1]);
-        const bool qvalid = (q >= 0) && (q < H);
+        const float rinv = (BORDER && (q < 0 || q >= H)) ? -INFINITY : 0.0f;
         float Rn[6];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -175,64 +177,81 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
             float v;
             if (!kFma) v = (A * C - B * B) - (k * (A + C)) * (A + C);
             else v = (A * C - B * B) - k * ((A + C) * (A + C));
-            Rn[i + 1] = (qvalid && cvalid[i]) ? v : -INFINITY;       // dilate ignores pixels outside the image
+            // dilate ignores pixels outside the image: -inf there (v + 0 is exact, v - inf = -inf)
+            Rn[i + 1] = BORDER ? v + (cinv[i] + rinv) : v;
         }
         Rn[0] = __shfl_up_sync(0xffffffffu, Rn[4], 1);
         Rn[5] = __shfl_down_sync(0xffffffffu, Rn[1], 1);
-        if (lane == 0) Rn[0] = -INFINITY;
-        if (lane == 31) Rn[5] = -INFINITY;
-        if (response && qvalid && q >= y0 && q < y0 + HR_ROWS && lane >= 1 && lane <= 30) {
+        if (response) {
+            if (out_lane && q >= y0 && q < y0 + rows) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (cvalid[i]) response[((size_t)b * H + q) * W + c0 + i] = Rn[i + 1];
-        }
-        // ---- NMS for row n = q-1: rows Rm (n-1, already reduced to hmax3), Rc (n), Rn (n+1)
-        const int n = q - 1;
-        unsigned long long key[4];
-        unsigned cmask = 0;
-        const bool nrow_ok = (n >= y0) && (n < y0 + HR_ROWS) && (n >= 1) && (n < H - 1) && lane >= 1 && lane <= 30;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float hn = fmaxf(fmaxf(Rn[i], Rn[i + 1]), Rn[i + 2]);
-            const float v = Rc[i + 1];
-            const float m = fmaxf(fmaxf(Rm[i + 1], hn), fmaxf(Rc[i], Rc[i + 2]));
-            const int x = c0 + i;
-            if (nrow_ok && v > 0.0f && v >= m && x >= 1 && x < W - 1) {
-                cmask |= 1u << i;
-                key[i] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(n * W + x);
+                for (int i = 0; i < 4; ++i)
+                    if (!BORDER || (c0 + i >= 0 && c0 + i < W)) resp_row[i] = Rn[i + 1];
             }
-            if (n >= y0 && n < y0 + HR_ROWS && lane >= 1 && lane <= 30) tmax = fmaxf(tmax, v);   // -inf outside the image never wins
+            resp_row += W;
         }
+        // ---- NMS for row n = q-1: rows Rm (n-1, reduced to hmax3), Rc (n), Rn (n+1)
+        const int n = q - 1;
+        const bool nrow_ok = (n >= y0) && (n < y0 + rows) && (!BORDER || ((n >= 1) && (n < H - 1)));
+        if (n >= y0 && n < y0 + rows) {
+            unsigned cmask = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float hn = fmaxf(fmaxf(Rn[i], Rn[i + 1]), Rn[i + 2]);
+                const float v = Rc[i + 1];
+                const float m = fmaxf(fmaxf(Rm[i + 1], hn), fmaxf(Rc[i], Rc[i + 2]));
+                const float ve = v + cemit[i];               // -inf where this lane/column may not emit
+                if (ve > 0.0f && ve >= m) cmask |= 1u << i;
+                if (out_lane) tmax = fmaxf(tmax, v);         // -inf outside the image never wins
+            }
+            if (cmask && nrow_ok) {
+                // stage the keys: shared-memory atomic slot allocation, flushed by the warp when filling up
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (cmask & (1u << i)) {
+                        const unsigned pos = atomicAdd(cnt, 1u);
+                        buf[pos] = ((unsigned long long)__float_as_uint(Rc[i + 1]) << 32) | (addr_row + (unsigned)i);
+                    }
+            }
+            __syncwarp();
+            if (*cnt > (unsigned)(HW_BUF - 128)) flush();    // warp-uniform: a step adds at most 120 keys
+        }
+        addr_row += (unsigned)W;
         // roll the response rows: Rm <- hmax3(Rc), Rc <- Rn
 #pragma unroll
         for (int i = 0; i < 4; ++i) Rm[i + 1] = fmaxf(fmaxf(Rc[i], Rc[i + 1]), Rc[i + 2]);
 #pragma unroll
         for (int i = 0; i < 6; ++i) Rc[i] = Rn[i];
-        // ---- stage candidates (warp-aggregated, no atomics until a flush)
-        const int mine = __popc(cmask);
-        if (__any_sync(0xffffffffu, mine != 0)) {
-            int pre = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, pre, d);
-                if (lane >= d) pre += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, pre, 31);
-            if (nbuf + tot > HW_BUF) flush();
-            int pos = nbuf + pre - mine;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (cmask & (1u << i)) buf[pos++] = key[i];
-            nbuf += tot;
-            __syncwarp();
-        }
         // ---- roll the row terms
 #pragma unroll
         for (int i = 0; i < 4; ++i) { dA[i] = dB[i]; dB[i] = dN[i]; sA[i] = sB[i]; sB[i] = sN[i]; }
     }
-    if (nbuf) flush();
+    __syncwarp();
+    if (*cnt) flush();
     const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
     if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
+}
+
+template <bool kFma>
+__global__ void __launch_bounds__(HW_WARPS * 32)
+harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
+                  int n_items) {
+    __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
+    __shared__ unsigned s_cnt[HW_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * HW_WARPS + warp;
+    if (item >= n_items) return;
+    const int b = blockIdx.y, slot = slots.v[b];
+    const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
+    const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * HR_ROWS;
+    const uint8_t *org = pyr.image_origin(0, slot);
+    if (lane == 0) s_cnt[warp] = 0u;
+    __syncwarp();
+    // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+HR_ROWS+2 all inside the image, and the
+    // outputs stay off the 1-px frame
+    const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + HR_ROWS + 2 < H);
+    if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+    else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, k, det, b, response, s_buf[warp], &s_cnt[warp]);
 }
 
 __global__ void detect_reset_kernel(DetectScratch det, int n) {
