@@ -378,8 +378,17 @@ def main_b200(args, wl):
         dom = max(prof, key=lambda kname: prof[kname]["ms_per_step"])
         per_launch_bytes = stage_bytes.get(dom, 0) * S / max(prof[dom]["launches_per_step"], 1)
         ach = per_launch_bytes / (prof[dom]["us_per_launch"] * 1e-6) / 1e9 if prof[dom]["us_per_launch"] > 0 else 0.0
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+            for kname, v in tj.items():
+                if kname.startswith(dom) and args.workload == "euroc" and S == 64:
+                    traffic = v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]
+        except Exception:
+            traffic = None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "note": "LK and Harris are instruction-issue-bound, not HBM-bound (ncu: profiles/, DESIGN.md section 4)",
                     "algorithmic_bytes_per_launch": per_launch_bytes, "us_per_launch": prof[dom]["us_per_launch"],
                     "share_of_step": prof[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in prof.values()), 1e-12)}
     step_frac = (value / world) * total_bytes / 1e9 / hbm_peak
