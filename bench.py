@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--ring", type=int, default=8, help="distinct frames per stream kept resident")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--undistort", action="store_true",
+                    help="also run cv::undistort's remap in front of preprocess (SURVEY 8(f) rank 1; not the headline config)")
     ap.add_argument("--profile-steps", type=int, default=20, help="extra steps with per-kernel events")
     return ap.parse_args()
 
@@ -160,6 +162,7 @@ def workload_config(args, wl, n_gpus):
                         f"Harris-GFTT q=1e-3 minDist 20, Poisson radius 20, LK (30, 0.01)",
             "streams_per_gpu": args.streams, "global_streams": args.streams * n_gpus, "ring_frames": args.ring,
             "parallelism": f"streams partitioned across {n_gpus} GPU(s), no collective",
+            "undistort": bool(getattr(args, "undistort", False)),
             "l2": f"inputs larger than L2: {args.streams}x{args.ring} resident frames = "
                   f"{args.streams * args.ring * wl['width'] * wl['height'] / 1e6:.0f} MB cycled (L2 126 MB)"}
 
@@ -208,6 +211,10 @@ def main_b200(args, wl):
     slots = [np.array([fe.acquire() for _ in range(S)], np.int32) for _ in range(NSETS)]
     slotsA = slots[0]
     N.check(L.rdfe_set_pipelining(h, 1), "set_pipelining")
+    if args.undistort:
+        sc = W / 752.0
+        fe.set_undistort(np.array([[458.654 * sc, 0, 367.215 * sc], [0, 457.296 * sc, 248.375 * H / 480.0], [0, 0, 1]], np.float32),
+                         np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32))
 
     # ---- resident inputs: frames [S][T][H][W] in HBM (and pinned on the host for e2e)
     host_frames = torch.empty((S, T, H, W), dtype=torch.uint8, pin_memory=True)

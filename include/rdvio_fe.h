@@ -158,6 +158,13 @@ RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const 
                            const int *dev_track_counts, char *dev_status, const rdfe_detect_params *dp,
                            int *dev_kp_counts, int stride);
 
+/* "Next" row: the cv::undistort(img, out, K, D) the reference's dataset reader applies to
+ * every frame before addFrame (examples/dataset.hpp:232-236, :591).  K: 3x3 row-major float32 camera matrix,
+ * D: k1 k2 p1 p2 float32.  When set, every preprocess / frontend_step call first remaps its source frames with
+ * OpenCV's exact fixed-point bilinear arithmetic (bit-identical to cv::undistort); NULL, NULL switches it off.
+ * One calibration per context (all streams of a context share the camera model). */
+RDFE_API int rdfe_set_undistort(rdfe_ctx *ctx, const float *K, const float *D);
+
 /* Cross-step pipelining for rdfe_frontend_step_dev (off by default).  When on, the preprocess stage of a call
  * runs on an internal stream and only waits for the step BEFORE the previous one, so it overlaps the previous
  * step's tracking/detection -- provided its new slots were not touched by the previous step (use three slot
@@ -179,7 +186,8 @@ RDFE_API int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy,
 
 /* ---- parity / debugging taps (not on the hot path) ---------------------- */
 /* plane: 0 = 8-bit image (w*h bytes), 1 = Scharr derivative (w*h*2 int16),
- * 2 = image with its win-px REFLECT_101 halo ((w+2win)*(h+2win) bytes). */
+ * 2 = image with its win-px REFLECT_101 halo ((w+2win)*(h+2win) bytes),
+ * 3 = (level 0 only) the undistorted frame before CLAHE, if rdfe_set_undistort is active (w*h bytes). */
 RDFE_API int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst, size_t dst_bytes);
 RDFE_API int rdfe_download_clahe_lut(rdfe_ctx *ctx, int batch_index, uint8_t *dst, size_t dst_bytes);
 /* Harris response map of the slot's level-0 image (w*h floats). */

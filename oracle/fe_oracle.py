@@ -203,3 +203,26 @@ def track_keypoints(curr: Pyramid, nxt: Pyramid, curr_xy, pred_xy=None, win=21, 
     H, W = curr.shape
     lib().orc_track_keypoints(curr._h, nxt._h, W, H, _p(c), _p(q), int(has_pred), _p(st), n, win, max_level, _p(fwd))
     return q, st, fwd
+
+
+# ------------------------------------------------------------------ undistort
+def undistort_map(W, H, K, D):
+    """Fixed-point map of cv::undistort(src, dst, K, D) (K 3x3, D = k1 k2 p1 p2; both as float32 like the reference)."""
+    L = lib()
+    L.orc_undistort_map.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_remap_bilinear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    D = np.ascontiguousarray(D, np.float32).reshape(-1)[:4]
+    mxy = np.empty((H, W, 2), np.int16)
+    mf = np.empty((H, W), np.uint16)
+    L.orc_undistort_map(W, H, _p(K), _p(D), _p(mxy), _p(mf))
+    return mxy, mf
+
+
+def undistort(img, K, D):
+    img = _u8(img)
+    H, W = img.shape
+    mxy, mf = undistort_map(W, H, K, D)
+    dst = np.empty_like(img)
+    lib().orc_remap_bilinear(_p(img), W, H, W, _p(mxy), _p(mf), _p(dst), W)
+    return dst

@@ -136,6 +136,35 @@ static int check_slots(const rdfe_ctx *ctx, const int *slots, int n, SlotList *o
 
 static inline const SlotList &sl_copy(const SlotList &s) { return s; }
 
+static int check_launch(rdfe_ctx *ctx, int launched, const char *what);
+
+// Copies the source pointer array to the device and, if undistortion is on, remaps every frame into the
+// per-slot undistorted plane first.  Returns the device pointer array / pitch the CLAHE kernels must read.
+static int stage_sources(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *const *dev_images, size_t pitch,
+                         const uint8_t *const **d_src_out, size_t *pitch_out, int *vec4_out) {
+    cudaStream_t st = ctx->ls;
+    int vec4 = (pitch % 4 == 0) ? 1 : 0;
+    for (int i = 0; i < n; ++i) {
+        if (!dev_images[i]) { set_error("image %d is null", i); return RDFE_ERR_INVALID; }
+        if ((uintptr_t)dev_images[i] % 4) vec4 = 0;
+    }
+    if (!ctx->und_on) {
+        RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, st));
+        *d_src_out = ctx->d_srcptrs; *pitch_out = pitch; *vec4_out = vec4;
+        return RDFE_OK;
+    }
+    const uint8_t *ptrs[2 * RDFE_MAX_BATCH];
+    for (int i = 0; i < n; ++i) {
+        ptrs[i] = dev_images[i];
+        ptrs[RDFE_MAX_BATCH + i] = ctx->und_plane + (size_t)slots[i] * ctx->raw_slot;
+    }
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, st));
+    int rc = check_launch(ctx, launch_undistort(ctx, n, ctx->d_srcptrs, pitch, (uint8_t *const *)(ctx->d_srcptrs + RDFE_MAX_BATCH), ctx->raw_pitch), "undistort");
+    if (rc) return rc;
+    *d_src_out = ctx->d_srcptrs + RDFE_MAX_BATCH; *pitch_out = ctx->raw_pitch; *vec4_out = 1;
+    return RDFE_OK;
+}
+
 static int check_launch(rdfe_ctx *ctx, int launched, const char *what) {
     if (launched < 0) return launched;
     cudaError_t e = cudaGetLastError();
@@ -254,7 +283,7 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->d_gftt_xy, npts * 2 * sizeof(float)));
     CK(cudaMalloc(&ctx->d_gftt_resp, npts * sizeof(float)));
     CK(cudaMalloc(&ctx->d_gftt_counts, RDFE_MAX_BATCH * sizeof(int)));
-    CK(cudaMalloc(&ctx->d_srcptrs, RDFE_MAX_BATCH * sizeof(uint8_t *)));
+    CK(cudaMalloc(&ctx->d_srcptrs, 2 * RDFE_MAX_BATCH * sizeof(uint8_t *)));
     if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     ctx->ls = ctx->stream;
@@ -268,7 +297,7 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_step_done[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_step_done[1], cudaEventDisableTiming));
     CK(cudaMalloc(&ctx->lut2, (size_t)RDFE_MAX_BATCH * kMaxTiles * kMaxTiles * 256));
-    CK(cudaMalloc(&ctx->d_srcptrs2, RDFE_MAX_BATCH * sizeof(uint8_t *)));
+    CK(cudaMalloc(&ctx->d_srcptrs2, 2 * RDFE_MAX_BATCH * sizeof(uint8_t *)));
     CK(cudaMalloc(&ctx->d_gftt_xy2, npts * 2 * sizeof(float)));
     CK(cudaMalloc(&ctx->d_gftt_resp2, npts * sizeof(float)));
     CK(cudaMalloc(&ctx->d_gftt_counts2, RDFE_MAX_BATCH * sizeof(int)));
@@ -303,7 +332,7 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int l = 0; l < RDFE_MAX_LEVELS; ++l) { cudaFree(ctx->pyr.img[l]); cudaFree(ctx->pyr.der[l]); }
-    cudaFree(ctx->raw); cudaFree(ctx->lut);
+    cudaFree(ctx->raw); cudaFree(ctx->lut); cudaFree(ctx->und_map_xy); cudaFree(ctx->und_map_f); cudaFree(ctx->und_plane);
     cudaFree(ctx->det.cand); cudaFree(ctx->det.cand2); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.overflow);
     cudaFree(ctx->d_xy_a); cudaFree(ctx->d_xy_b); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->d_gftt_xy); cudaFree(ctx->d_gftt_resp); cudaFree(ctx->d_gftt_counts); cudaFree(ctx->d_srcptrs);
@@ -390,15 +419,14 @@ int rdfe_preprocess_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const uint
     ClaheParams cp;
     rc = make_clahe_params(ctx, clip_limit, tiles_x, tiles_y, &cp);
     if (rc) return rc;
-    int vec4 = (pitch % 4 == 0) ? 1 : 0;
-    for (int i = 0; i < n; ++i) {
-        if (!dev_images[i]) { set_error("rdfe_preprocess_batch_dev: image %d is null", i); return RDFE_ERR_INVALID; }
-        if ((uintptr_t)dev_images[i] % 4) vec4 = 0;
-    }
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
-    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t *const *d_src = nullptr;
+    size_t spitch = 0;
+    int vec4 = 0;
+    rc = stage_sources(ctx, slots, n, dev_images, pitch, &d_src, &spitch, &vec4);
+    if (rc) return rc;
     ctx->last_clahe_tiles = tiles_x * tiles_y;
-    rc = check_launch(ctx, launch_clahe(ctx, sl, ctx->d_srcptrs, pitch, vec4, cp), "clahe");
+    rc = check_launch(ctx, launch_clahe(ctx, sl, d_src, spitch, vec4, cp), "clahe");
     if (rc) return rc;
     return check_launch(ctx, launch_pyramid(ctx, sl), "pyramid");
 }
@@ -577,10 +605,12 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     auto restore = [&]() { ctx->lut = lut_keep; ctx->d_srcptrs = src_keep; ctx->ls = ctx->stream; };
     // ---- preprocess: CLAHE (level 0 + halo), pyramid, Scharr
     ctx->ls = ps;
-    cudaError_t ce = cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, ps);
-    if (ce != cudaSuccess) { restore(); set_error("rdfe_frontend_step_dev: %s", cudaGetErrorString(ce)); return RDFE_ERR_CUDA; }
+    const uint8_t *const *d_src = nullptr;
+    size_t spitch = 0;
+    rc = stage_sources(ctx, new_slots, n, dev_images, pitch, &d_src, &spitch, &vec4);
+    if (rc) { restore(); return rc; }
     ctx->last_clahe_tiles = tiles_x * tiles_y;
-    rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), ctx->d_srcptrs, pitch, vec4, cp), "clahe");
+    rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), d_src, spitch, vec4, cp), "clahe");
     if (rc) { restore(); return rc; }
     cudaEventRecord(ctx->ev_clahe_done, ps);
     cudaEventRecord(ctx->ev_apply_done, ps);
@@ -613,6 +643,27 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     memset(ctx->last_step_slots, 0, (size_t)ctx->cfg.num_slots);
     for (int i = 0; i < n; ++i) { ctx->last_step_slots[new_slots[i]] = 1; if (prev_slots) ctx->last_step_slots[prev_slots[i]] = 1; }
     ctx->step_index++;
+    return RDFE_OK;
+}
+
+int rdfe_set_undistort(rdfe_ctx *ctx, const float *K, const float *D) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    int rc = rdfe_sync(ctx);
+    if (rc) return rc;
+    if (!K || !D) { ctx->und_on = false; return RDFE_OK; }
+    const int W = ctx->cfg.width, H = ctx->cfg.height;
+    std::vector<uint32_t> mxy;
+    std::vector<uint16_t> mf;
+    build_undistort_map(W, H, K, D, mxy, mf);
+    if (!ctx->und_map_xy) {
+        RDFE_CUDA_OK(cudaMalloc(&ctx->und_map_xy, (size_t)W * H * sizeof(uint32_t)));
+        RDFE_CUDA_OK(cudaMalloc(&ctx->und_map_f, (size_t)W * H * sizeof(uint16_t)));
+        RDFE_CUDA_OK(cudaMalloc(&ctx->und_plane, ctx->raw_slot * ctx->cfg.num_slots));
+    }
+    RDFE_CUDA_OK(cudaMemcpy(ctx->und_map_xy, mxy.data(), mxy.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RDFE_CUDA_OK(cudaMemcpy(ctx->und_map_f, mf.data(), mf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    ctx->und_on = true;
     return RDFE_OK;
 }
 
@@ -738,6 +789,9 @@ int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst
         if (dst_bytes < fw * fh) { set_error("rdfe_download_level: buffer too small"); return RDFE_ERR_INVALID; }
         const uint8_t *src = ctx->pyr.image_origin(level, slot) - (size_t)win * g.ipitch - win;
         RDFE_CUDA_OK(cudaMemcpy2D(dst, fw, src, g.ipitch, fw, fh, cudaMemcpyDeviceToHost));
+    } else if (plane == 3 && level == 0 && ctx->und_on) {
+        if (dst_bytes < (size_t)g.w * g.h) { set_error("rdfe_download_level: buffer too small"); return RDFE_ERR_INVALID; }
+        RDFE_CUDA_OK(cudaMemcpy2D(dst, g.w, ctx->und_plane + (size_t)slot * ctx->raw_slot, ctx->raw_pitch, g.w, g.h, cudaMemcpyDeviceToHost));
     } else {
         set_error("rdfe_download_level: plane %d unknown", plane);
         return RDFE_ERR_INVALID;
@@ -816,8 +870,8 @@ int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t b
     return RDFE_OK;
 }
 
-static const char *const kKernelNames[K_COUNT] = {"clahe_hist_lut", "clahe_apply", "pyrdown", "scharr", "halo",
-                                                  "harris_nms", "select", "lk_track", "poisson_append"};
+static const char *const kKernelNames[K_COUNT] = {"clahe_hist_lut", "clahe_apply", "pyrdown", "scharr",
+                                                  "harris_nms", "select", "lk_track", "poisson_append", "undistort"};
 
 int rdfe_profile_num_kernels(void) { return K_COUNT; }
 const char *rdfe_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }

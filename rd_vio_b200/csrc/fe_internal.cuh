@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/rdvio_fe.h"
 
 namespace rdfe {
@@ -105,7 +107,7 @@ struct ClaheParams {
 };
 
 enum KernelId {
-    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HALO, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_COUNT
+    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_COUNT
 };
 constexpr int kProfMax = 4096;      // timed launches between two rdfe_profile_collect calls
 
@@ -133,6 +135,11 @@ struct rdfe_ctx {
     bool overlap;                 // rdfe_frontend_step*: run Harris + selection on aux_stream beside pyramid + LK
     cudaStream_t aux_stream;      // detection branch of rdfe_frontend_step*
     cudaEvent_t ev_fork, ev_join;
+    // optional undistortion in front of preprocess (rdfe_set_undistort): fixed-point remap tables + output staging
+    bool und_on;
+    uint32_t *und_map_xy;         // [H][W] (sx | sy << 16), int16 each
+    uint16_t *und_map_f;          // [H][W] fy*32 + fx
+    uint8_t *und_plane;           // [num_slots][H][raw_pitch] undistorted frames
     // cross-step pipelining (rdfe_set_pipelining): preprocess of step s+1 on pre_stream beside track/detect of step s
     bool pipeline_steps;
     cudaStream_t pre_stream;
@@ -182,6 +189,7 @@ struct rdfe_ctx {
 namespace rdfe {
 
 void set_error(const char *fmt, ...);
+void build_undistort_map(int W, int H, const float *K, const float *D, std::vector<uint32_t> &mxy, std::vector<uint16_t> &mf);
 #define RDFE_CUDA_OK(expr)                                                            \
     do {                                                                              \
         cudaError_t e__ = (expr);                                                     \
@@ -222,6 +230,8 @@ int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_det
                        float *d_gftt_resp, int *d_gftt_counts);
 int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, const float *d_gftt_xy,
                           const int *d_gftt_counts, double *d_xy, int *d_counts, int stride);
+int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t src_pitch, uint8_t *const *d_dst,
+                     size_t dst_pitch);
 int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const rdfe_track_params &p,
               const double *d_curr_xy, double *d_next_xy, const int *d_counts, int stride, char *d_status);
 

@@ -74,6 +74,15 @@ class FrontEnd:
     def kernel_launches(self) -> int:
         return int(self._L.rdfe_kernel_launches(self._h))
 
+    def set_undistort(self, K=None, D=None):
+        """cv::undistort(img, out, K, D) in front of every preprocess (examples/dataset.hpp:232-236); None switches off."""
+        if K is None or D is None:
+            N.check(self._L.rdfe_set_undistort(self._h, None, None), "rdfe_set_undistort")
+            return
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        D = np.ascontiguousarray(np.asarray(D, np.float32).reshape(-1)[:4])
+        N.check(self._L.rdfe_set_undistort(self._h, _vp(K), _vp(D)), "rdfe_set_undistort")
+
     # -- batched host-pointer API
     def preprocess(self, slots: Sequence[int], images: Sequence[np.ndarray], clip_limit=6.0, tiles=(8, 8)):
         n = len(slots)
@@ -158,6 +167,8 @@ class FrontEnd:
             out = np.empty((h, w), np.uint8)
         elif plane == 1:
             out = np.empty((h, w, 2), np.int16)
+        elif plane == 3:
+            out = np.empty((h, w), np.uint8)
         else:
             out = np.empty((h + 2 * self.win, w + 2 * self.win), np.uint8)
         N.check(self._L.rdfe_download_level(self._h, slot, level, plane, _vp(out), out.nbytes), "rdfe_download_level")

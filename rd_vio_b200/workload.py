@@ -41,8 +41,8 @@ def algorithmic_bytes(width, height, points, max_level, win):
         "scharr": 5 * P,
         "harris_nms": S,
         "lk_track": 12 * U + 64 * points,
-        "halo": 0,
         "select": 0,
+        "poisson_append": 0,
     }
     return sum(stages.values()), stages
 

@@ -344,3 +344,24 @@ def test_cross_step_pipelining_equals_serial(stream0, frames0):
         assert np.array_equal(a[2], b[2]), f"step {s}: status differs"
         for i in range(n):
             assert np.array_equal(a[0][i, :a[1][i]], b[0][i, :b[1][i]]), f"step {s} image {i}"
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (257, 331)])
+def test_undistort_bit_exact(orc, shape):
+    """rdfe_set_undistort: cv::undistort's fixed-point remap in front of preprocess (SURVEY 8(f) rank 1)."""
+    from rd_vio_b200.frontend import FrontEnd
+    H, W = shape
+    img = random_image(H, W, seed=3 * W)
+    s = W / 752.0
+    K = np.array([[458.654 * s, 0, 367.215 * s], [0, 457.296 * s, 248.375 * H / 480.0], [0, 0, 1]], np.float32)
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+    want = orc.undistort(img, K, D)
+    with FrontEnd(W, H, max_level=2, win=21, num_slots=2, max_points=64) as fe:
+        fe.set_undistort(K, D)
+        s0 = fe.acquire()
+        fe.preprocess([s0], [img])
+        assert np.array_equal(fe.download_level(s0, 0, 3), want), "undistorted frame differs"
+        assert np.array_equal(fe.download_level(s0, 0, 0), orc.clahe(want)), "CLAHE(undistort) differs"
+        fe.set_undistort(None, None)
+        fe.preprocess([s0], [img])
+        assert np.array_equal(fe.download_level(s0, 0, 0), orc.clahe(img))

@@ -87,3 +87,11 @@ def test_poisson_filter_literal_loop():
                 pts.append(c)
                 want.append(c)
         assert np.array_equal(got, np.array(want).reshape(-1, 2))
+
+
+def test_undistort_golden():
+    """SURVEY 8(f) rank 1: cv::undistort in front of the plugin (examples/dataset.hpp:232-236)."""
+    U = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_undistort_v1.npz"))
+    out = orc.undistort(G["f0"], U["K"], U["D"])
+    assert np.array_equal(out[::30], U["rows"])
+    assert sha(out) == str(U["undistorted_sha"])

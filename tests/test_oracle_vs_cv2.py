@@ -53,3 +53,14 @@ def test_track_vs_cv2(stream0, frames0):
         assert (s_cv == s_or).mean() >= 0.995
         ok = (s_cv != 0) & (s_or != 0)
         assert ok.sum() > 100 and np.abs(n_cv[ok] - n_or[ok]).max() <= 0.01
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (720, 1280), (257, 331)])
+def test_undistort_vs_cv2(shape):
+    import cv2
+    H, W = shape
+    img = random_image(H, W, seed=W)
+    s = W / 752.0
+    K = np.array([[458.654 * s, 0, 367.215 * s], [0, 457.296 * s, 248.375 * H / 480.0], [0, 0, 1]], np.float32)
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+    assert np.array_equal(cv2.undistort(img, K, D), orc.undistort(img, K, D))
