@@ -165,6 +165,12 @@ RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const 
  * One calibration per context (all streams of a context share the camera model). */
 RDFE_API int rdfe_set_undistort(rdfe_ctx *ctx, const float *K, const float *D);
 
+/* "Next" row: Odometry::addFrame's cv::cvtColor(BGR2GRAY / BGRA2GRAY) (rdvio.hpp:42-49).
+ * channels = 1 (default, gray), 3 (BGR) or 4 (BGRA): source frames of all later preprocess / frontend_step calls
+ * are `width * channels` bytes per row; colour frames are converted with OpenCV's 15-bit fixed-point weights
+ * (bit-identical to cv::cvtColor), after the optional undistortion (which then runs per channel). */
+RDFE_API int rdfe_set_input_format(rdfe_ctx *ctx, int channels);
+
 /* Cross-step pipelining for rdfe_frontend_step_dev (off by default).  When on, the preprocess stage of a call
  * runs on an internal stream and only waits for the step BEFORE the previous one, so it overlaps the previous
  * step's tracking/detection -- provided its new slots were not touched by the previous step (use three slot

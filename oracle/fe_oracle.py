@@ -226,3 +226,18 @@ def undistort(img, K, D):
     dst = np.empty_like(img)
     lib().orc_remap_bilinear(_p(img), W, H, W, _p(mxy), _p(mf), _p(dst), W)
     return dst
+
+
+# ------------------------------------------------------------------ gray conversion
+def bgr2gray(img):
+    """cv::cvtColor(img, COLOR_BGR2GRAY / COLOR_BGRA2GRAY) for 8-bit (Odometry::addFrame, rdvio.hpp:42-49):
+    15-bit fixed point (B*3735 + G*19235 + R*9798 + 2^14) >> 15."""
+    img = np.ascontiguousarray(img, np.uint8)
+    b, g, r = (img[..., i].astype(np.int64) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def undistort_color(img, K, D):
+    """cv::undistort on a 3/4-channel frame: the same remap per channel (alpha, if any, is dropped here)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    return np.stack([undistort(np.ascontiguousarray(img[..., c]), K, D) for c in range(3)], -1)

@@ -57,6 +57,7 @@ SYMBOLS = {
     "rdfe_frontend_step_dev": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _d, _i, _i, C.POINTER(TrackParams), _vp, _vp, _vp, _vp,
                                     C.POINTER(DetectParams), _vp, _i]),
     "rdfe_set_undistort": (_i, [_vp, _vp, _vp]),
+    "rdfe_set_input_format": (_i, [_vp, _i]),
     "rdfe_set_pipelining": (_i, [_vp, _i]),
     "rdfe_frontend_step_submit": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _d, _i, _i, C.POINTER(TrackParams), _vp, _vp, _vp,
                                        C.POINTER(DetectParams), _i, C.POINTER(_i)]),

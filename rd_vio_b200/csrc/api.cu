@@ -148,7 +148,7 @@ static int stage_sources(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *
         if (!dev_images[i]) { set_error("image %d is null", i); return RDFE_ERR_INVALID; }
         if ((uintptr_t)dev_images[i] % 4) vec4 = 0;
     }
-    if (!ctx->und_on) {
+    if (!ctx->und_on && ctx->in_channels == 1) {
         RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, dev_images, n * sizeof(uint8_t *), cudaMemcpyHostToDevice, st));
         *d_src_out = ctx->d_srcptrs; *pitch_out = pitch; *vec4_out = vec4;
         return RDFE_OK;
@@ -156,12 +156,12 @@ static int stage_sources(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *
     const uint8_t *ptrs[2 * RDFE_MAX_BATCH];
     for (int i = 0; i < n; ++i) {
         ptrs[i] = dev_images[i];
-        ptrs[RDFE_MAX_BATCH + i] = ctx->und_plane + (size_t)slots[i] * ctx->raw_slot;
+        ptrs[RDFE_MAX_BATCH + i] = ctx->und_plane + (size_t)slots[i] * ctx->gray_slot;
     }
     RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, st));
-    int rc = check_launch(ctx, launch_undistort(ctx, n, ctx->d_srcptrs, pitch, (uint8_t *const *)(ctx->d_srcptrs + RDFE_MAX_BATCH), ctx->raw_pitch), "undistort");
+    int rc = check_launch(ctx, launch_undistort(ctx, n, ctx->d_srcptrs, pitch, (uint8_t *const *)(ctx->d_srcptrs + RDFE_MAX_BATCH), ctx->gray_pitch), "ingest");
     if (rc) return rc;
-    *d_src_out = ctx->d_srcptrs + RDFE_MAX_BATCH; *pitch_out = ctx->raw_pitch; *vec4_out = 1;
+    *d_src_out = ctx->d_srcptrs + RDFE_MAX_BATCH; *pitch_out = ctx->gray_pitch; *vec4_out = 1;
     return RDFE_OK;
 }
 
@@ -264,6 +264,9 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
         CK(cudaMalloc(&pyr.der[l], pyr.lv[l].dslot * cfg->num_slots));
         CK(cudaMemset(pyr.der[l], 0, pyr.lv[l].dslot * cfg->num_slots));
     }
+    ctx->in_channels = 1;
+    ctx->gray_pitch = align_up((size_t)cfg->width, 4);
+    ctx->gray_slot = align_up(ctx->gray_pitch * cfg->height, 256);
     ctx->raw_pitch = align_up((size_t)cfg->width, 4);   // tight: a contiguous host image uploads as ONE 1-D copy
     ctx->raw_slot = align_up(ctx->raw_pitch * cfg->height, 256);
     CK(cudaMalloc(&ctx->raw, ctx->raw_slot * cfg->num_slots));
@@ -415,7 +418,7 @@ int rdfe_preprocess_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const uint
     SlotList sl;
     int rc = check_slots(ctx, slots, n, &sl, "rdfe_preprocess_batch_dev");
     if (rc) return rc;
-    if (!dev_images || pitch < (size_t)ctx->cfg.width) { set_error("rdfe_preprocess_batch_dev: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
+    if (!dev_images || pitch < (size_t)ctx->cfg.width * ctx->in_channels) { set_error("rdfe_preprocess_batch_dev: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
     ClaheParams cp;
     rc = make_clahe_params(ctx, clip_limit, tiles_x, tiles_y, &cp);
     if (rc) return rc;
@@ -436,7 +439,7 @@ int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n, const uint8_t 
     SlotList sl;
     int rc = check_slots(ctx, slots, n, &sl, "rdfe_preprocess_batch");
     if (rc) return rc;
-    if (!images || pitch < (size_t)ctx->cfg.width) { set_error("rdfe_preprocess_batch: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
+    if (!images || pitch < (size_t)ctx->cfg.width * ctx->in_channels) { set_error("rdfe_preprocess_batch: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
     std::vector<const uint8_t *> dptr(n);
     for (int i = 0; i < n; ++i) {
@@ -445,7 +448,7 @@ int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n, const uint8_t 
         if (pitch == ctx->raw_pitch)
             RDFE_CUDA_OK(cudaMemcpyAsync(d, images[i], pitch * (size_t)ctx->cfg.height, cudaMemcpyHostToDevice, ctx->stream));
         else
-            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width, (size_t)ctx->cfg.height,
+            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width * ctx->in_channels, (size_t)ctx->cfg.height,
                                            cudaMemcpyHostToDevice, ctx->stream));
         dptr[i] = d;
     }
@@ -578,7 +581,7 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     ClaheParams cp;
     rc = make_clahe_params(ctx, clip_limit, tiles_x, tiles_y, &cp);
     if (rc) return rc;
-    if (!dev_images || pitch < (size_t)ctx->cfg.width) { set_error("rdfe_frontend_step_dev: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
+    if (!dev_images || pitch < (size_t)ctx->cfg.width * ctx->in_channels) { set_error("rdfe_frontend_step_dev: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
     int vec4 = (pitch % 4 == 0) ? 1 : 0;
     for (int i = 0; i < n; ++i) {
         if (!dev_images[i]) { set_error("rdfe_frontend_step_dev: image %d is null", i); return RDFE_ERR_INVALID; }
@@ -659,11 +662,28 @@ int rdfe_set_undistort(rdfe_ctx *ctx, const float *K, const float *D) {
     if (!ctx->und_map_xy) {
         RDFE_CUDA_OK(cudaMalloc(&ctx->und_map_xy, (size_t)W * H * sizeof(uint32_t)));
         RDFE_CUDA_OK(cudaMalloc(&ctx->und_map_f, (size_t)W * H * sizeof(uint16_t)));
-        RDFE_CUDA_OK(cudaMalloc(&ctx->und_plane, ctx->raw_slot * ctx->cfg.num_slots));
     }
+    if (!ctx->und_plane) RDFE_CUDA_OK(cudaMalloc(&ctx->und_plane, ctx->gray_slot * ctx->cfg.num_slots));
     RDFE_CUDA_OK(cudaMemcpy(ctx->und_map_xy, mxy.data(), mxy.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     RDFE_CUDA_OK(cudaMemcpy(ctx->und_map_f, mf.data(), mf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     ctx->und_on = true;
+    return RDFE_OK;
+}
+
+int rdfe_set_input_format(rdfe_ctx *ctx, int channels) {
+    if (!ctx || (channels != 1 && channels != 3 && channels != 4)) { set_error("rdfe_set_input_format: channels must be 1, 3 (BGR) or 4 (BGRA)"); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    int rc = rdfe_sync(ctx);
+    if (rc) return rc;
+    if (channels == ctx->in_channels) return RDFE_OK;
+    // upload staging holds the frames as given (W * channels bytes per row)
+    cudaFree(ctx->raw);
+    ctx->raw = nullptr;
+    ctx->raw_pitch = align_up((size_t)ctx->cfg.width * channels, 4);
+    ctx->raw_slot = align_up(ctx->raw_pitch * ctx->cfg.height, 256);
+    RDFE_CUDA_OK(cudaMalloc(&ctx->raw, ctx->raw_slot * ctx->cfg.num_slots));
+    if (!ctx->und_plane) RDFE_CUDA_OK(cudaMalloc(&ctx->und_plane, ctx->gray_slot * ctx->cfg.num_slots));
+    ctx->in_channels = channels;
     return RDFE_OK;
 }
 
@@ -689,7 +709,7 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
         return RDFE_ERR_INVALID;
     }
     if (prev_slots && (!tp || !curr_xy)) { set_error("rdfe_frontend_step_submit: tracking needs tp and curr_xy"); return RDFE_ERR_INVALID; }
-    if (pitch < (size_t)ctx->cfg.width) { set_error("rdfe_frontend_step_submit: pitch < width"); return RDFE_ERR_INVALID; }
+    if (pitch < (size_t)ctx->cfg.width * ctx->in_channels) { set_error("rdfe_frontend_step_submit: pitch < width * channels"); return RDFE_ERR_INVALID; }
     const int p = (int)(ctx->pl_ticket & 1);
     if (ctx->pl_busy[p]) { set_error("rdfe_frontend_step_submit: stage %d still holds un-waited results (at most 2 steps in flight)", p); return RDFE_ERR_INVALID; }
     for (int i = 0; i < n; ++i) {
@@ -710,7 +730,7 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
         if (pitch == ctx->raw_pitch)
             RDFE_CUDA_OK(cudaMemcpyAsync(d, images[i], pitch * (size_t)ctx->cfg.height, cudaMemcpyHostToDevice, ctx->copy_stream));
         else
-            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width, (size_t)ctx->cfg.height,
+            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width * ctx->in_channels, (size_t)ctx->cfg.height,
                                            cudaMemcpyHostToDevice, ctx->copy_stream));
         dptr[i] = d;
     }
@@ -789,9 +809,9 @@ int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst
         if (dst_bytes < fw * fh) { set_error("rdfe_download_level: buffer too small"); return RDFE_ERR_INVALID; }
         const uint8_t *src = ctx->pyr.image_origin(level, slot) - (size_t)win * g.ipitch - win;
         RDFE_CUDA_OK(cudaMemcpy2D(dst, fw, src, g.ipitch, fw, fh, cudaMemcpyDeviceToHost));
-    } else if (plane == 3 && level == 0 && ctx->und_on) {
+    } else if (plane == 3 && level == 0 && (ctx->und_on || ctx->in_channels > 1)) {
         if (dst_bytes < (size_t)g.w * g.h) { set_error("rdfe_download_level: buffer too small"); return RDFE_ERR_INVALID; }
-        RDFE_CUDA_OK(cudaMemcpy2D(dst, g.w, ctx->und_plane + (size_t)slot * ctx->raw_slot, ctx->raw_pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+        RDFE_CUDA_OK(cudaMemcpy2D(dst, g.w, ctx->und_plane + (size_t)slot * ctx->gray_slot, ctx->gray_pitch, g.w, g.h, cudaMemcpyDeviceToHost));
     } else {
         set_error("rdfe_download_level: plane %d unknown", plane);
         return RDFE_ERR_INVALID;

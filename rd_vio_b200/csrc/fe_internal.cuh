@@ -127,6 +127,7 @@ struct rdfe_ctx {
     rdfe::Pyramid pyr;
     uint8_t *raw;                 // upload staging slab [num_slots][H][raw_pitch]
     size_t raw_pitch, raw_slot;
+    size_t gray_pitch, gray_slot;  // geometry of the ingest output plane (und_plane)
     CUtensorMap tm_img[RDFE_MAX_LEVELS];
     CUtensorMap tm_der[RDFE_MAX_LEVELS];
     cudaStream_t stream;
@@ -136,6 +137,7 @@ struct rdfe_ctx {
     cudaStream_t aux_stream;      // detection branch of rdfe_frontend_step*
     cudaEvent_t ev_fork, ev_join;
     // optional undistortion in front of preprocess (rdfe_set_undistort): fixed-point remap tables + output staging
+    int in_channels;              // 1 gray (default), 3 BGR, 4 BGRA: cvtColor of Odometry::addFrame (rdvio.hpp:42-49)
     bool und_on;
     uint32_t *und_map_xy;         // [H][W] (sx | sy << 16), int16 each
     uint16_t *und_map_f;          // [H][W] fy*32 + fx

@@ -1,4 +1,4 @@
-// undistort.cu -- "next" row of the scope table: the cv::undistort(img, out, K, D) that the
+// undistort.cu -- ingest stage, "next" rows of the scope table: the cv::undistort(img, out, K, D) that the
 // reference's dataset reader applies to every frame before the Image plugin sees pixels
 // (/root/reference/examples/dataset.hpp:232-236, :591; dead twin OpenCvImage::correct_distortion,
 // src/rdvio_extra/src/opencv_image.cpp:163-177).
@@ -15,9 +15,16 @@
 
 namespace rdfe {
 
+// cv::cvtColor(BGR2GRAY / BGRA2GRAY) for 8-bit (rdvio.hpp:42-49): 15-bit fixed point,
+// (B*3735 + G*19235 + R*9798 + 2^14) >> 15 -- verified bit-exact against cv2 4.13.
+__device__ __forceinline__ int bgr_to_gray(int b, int g, int r) { return (b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15; }
+
+// Ingest kernel: optional undistortion (per channel, like cv::undistort on the loaded image) followed by the
+// optional gray conversion of Odometry::addFrame; writes the 8-bit gray frame CLAHE reads.
+template <int CH, bool UND>
 __global__ void __launch_bounds__(256)
-undistort_kernel(const uint8_t *const *__restrict__ src, size_t src_pitch, const uint32_t *__restrict__ map_xy,
-                 const uint16_t *__restrict__ map_f, uint8_t *const *__restrict__ dst, size_t dst_pitch, int W, int H) {
+ingest_kernel(const uint8_t *const *__restrict__ src, size_t src_pitch, const uint32_t *__restrict__ map_xy,
+              const uint16_t *__restrict__ map_f, uint8_t *const *__restrict__ dst, size_t dst_pitch, int W, int H) {
     const int groups = (W + 3) >> 2;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups * H) return;
@@ -28,26 +35,32 @@ undistort_kernel(const uint8_t *const *__restrict__ src, size_t src_pitch, const
     for (int i = 0; i < 4; ++i) {
         const int xi = x + i;
         if (xi >= W) break;
-        const size_t o = (size_t)y * W + xi;
-        const uint32_t m = __ldg(map_xy + o);
-        const unsigned f = __ldg(map_f + o);
-        const int sx = (int)(short)(m & 0xFFFFu), sy = (int)m >> 16;
-        const int fx = (int)(f & 31u), fy = (int)(f >> 5);
-        int p00 = 0, p01 = 0, p10 = 0, p11 = 0;                  // BORDER_CONSTANT, value 0
-        const bool x0 = (unsigned)sx < (unsigned)W, x1 = (unsigned)(sx + 1) < (unsigned)W;
-        if ((unsigned)sy < (unsigned)H) {
-            const uint8_t *r = img + (size_t)sy * src_pitch;
-            if (x0) p00 = __ldg(r + sx);
-            if (x1) p01 = __ldg(r + sx + 1);
+        int ch[3] = {0, 0, 0};
+        if (UND) {
+            const size_t o = (size_t)y * W + xi;
+            const uint32_t m = __ldg(map_xy + o);
+            const unsigned f = __ldg(map_f + o);
+            const int sx = (int)(short)(m & 0xFFFFu), sy = (int)m >> 16;
+            const int wx1 = (int)(f & 31u), wx0 = 32 - wx1, wy1 = (int)(f >> 5), wy0 = 32 - wy1;
+            const bool x0 = (unsigned)sx < (unsigned)W, x1 = (unsigned)(sx + 1) < (unsigned)W;
+            const bool y0 = (unsigned)sy < (unsigned)H, y1 = (unsigned)(sy + 1) < (unsigned)H;
+            const uint8_t *r0 = img + (size_t)sy * src_pitch + (size_t)sx * CH;
+            const uint8_t *r1 = r0 + src_pitch;
+#pragma unroll
+            for (int c = 0; c < (CH >= 3 ? 3 : 1); ++c) {
+                // BORDER_CONSTANT, value 0
+                const int p00 = (y0 && x0) ? __ldg(r0 + c) : 0, p01 = (y0 && x1) ? __ldg(r0 + CH + c) : 0;
+                const int p10 = (y1 && x0) ? __ldg(r1 + c) : 0, p11 = (y1 && x1) ? __ldg(r1 + CH + c) : 0;
+                const int v = ((p00 * wx0 + p01 * wx1) * wy0 + (p10 * wx0 + p11 * wx1) * wy1) * 32 + (1 << 14) >> 15;
+                ch[c] = min(v, 255);
+            }
+        } else {
+            const uint8_t *p = img + (size_t)y * src_pitch + (size_t)xi * CH;
+#pragma unroll
+            for (int c = 0; c < (CH >= 3 ? 3 : 1); ++c) ch[c] = __ldg(p + c);
         }
-        if ((unsigned)(sy + 1) < (unsigned)H) {
-            const uint8_t *r = img + (size_t)(sy + 1) * src_pitch;
-            if (x0) p10 = __ldg(r + sx);
-            if (x1) p11 = __ldg(r + sx + 1);
-        }
-        const int wx1 = fx, wx0 = 32 - fx, wy1 = fy, wy0 = 32 - fy;
-        const int v = ((p00 * wx0 + p01 * wx1) * wy0 + (p10 * wx0 + p11 * wx1) * wy1) * 32 + (1 << 14) >> 15;
-        out |= (unsigned)min(v, 255) << (8 * i);
+        const int v = (CH >= 3) ? bgr_to_gray(ch[0], ch[1], ch[2]) : ch[0];
+        out |= (unsigned)v << (8 * i);
     }
     uint8_t *d = dst[blockIdx.y] + (size_t)y * dst_pitch + x;
     if (x + 4 <= W) *reinterpret_cast<unsigned *>(d) = out;
@@ -59,8 +72,16 @@ int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t s
     const int W = ctx->cfg.width, H = ctx->cfg.height;
     const int groups = (W + 3) >> 2;
     dim3 grid((groups * H + 255) / 256, n);
-    RDFE_LAUNCH(ctx, K_UNDISTORT, (undistort_kernel<<<grid, 256, 0, ctx->ls>>>(d_src, src_pitch, ctx->und_map_xy, ctx->und_map_f,
-                                                                              d_dst, dst_pitch, W, H)));
+    const int ch = ctx->in_channels;
+#define RDFE_INGEST(CH, UND)                                                                                            \
+    RDFE_LAUNCH(ctx, K_UNDISTORT, (ingest_kernel<CH, UND><<<grid, 256, 0, ctx->ls>>>(d_src, src_pitch, ctx->und_map_xy,  \
+                                                                                   ctx->und_map_f, d_dst, dst_pitch, W, H)))
+    if (ctx->und_on) {
+        if (ch == 1) RDFE_INGEST(1, true); else if (ch == 3) RDFE_INGEST(3, true); else RDFE_INGEST(4, true);
+    } else {
+        if (ch == 3) RDFE_INGEST(3, false); else RDFE_INGEST(4, false);
+    }
+#undef RDFE_INGEST
     return 1;
 }
 

@@ -83,16 +83,23 @@ class FrontEnd:
         D = np.ascontiguousarray(np.asarray(D, np.float32).reshape(-1)[:4])
         N.check(self._L.rdfe_set_undistort(self._h, _vp(K), _vp(D)), "rdfe_set_undistort")
 
+    def set_input_format(self, channels: int):
+        """1 = gray (default), 3 = BGR, 4 = BGRA: cv::cvtColor of Odometry::addFrame (rdvio.hpp:42-49) on the device."""
+        N.check(self._L.rdfe_set_input_format(self._h, int(channels)), "rdfe_set_input_format")
+        self.channels = int(channels)
+
     # -- batched host-pointer API
     def preprocess(self, slots: Sequence[int], images: Sequence[np.ndarray], clip_limit=6.0, tiles=(8, 8)):
         n = len(slots)
+        ch = getattr(self, "channels", 1)
         imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        want = (self.height, self.width) if ch == 1 else (self.height, self.width, ch)
         for im in imgs:
-            if im.shape != (self.height, self.width):
-                raise ValueError(f"image shape {im.shape} != {(self.height, self.width)}")
+            if im.shape != want:
+                raise ValueError(f"image shape {im.shape} != {want}")
         sl = np.asarray(slots, np.int32)
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
-        N.check(self._L.rdfe_preprocess_batch(self._h, _vp(sl), n, ptrs, self.width, float(clip_limit),
+        N.check(self._L.rdfe_preprocess_batch(self._h, _vp(sl), n, ptrs, self.width * ch, float(clip_limit),
                                               int(tiles[0]), int(tiles[1])), "rdfe_preprocess_batch")
 
     def detect_params(self, **kw) -> N.DetectParams:

@@ -365,3 +365,24 @@ def test_undistort_bit_exact(orc, shape):
         fe.set_undistort(None, None)
         fe.preprocess([s0], [img])
         assert np.array_equal(fe.download_level(s0, 0, 0), orc.clahe(img))
+
+
+@pytest.mark.parametrize("channels,undistort", [(3, False), (4, False), (3, True), (4, True)])
+def test_color_ingest_bit_exact(orc, channels, undistort):
+    """rdfe_set_input_format: cvtColor(BGR/BGRA -> gray) of Odometry::addFrame on the device, optionally after the
+    per-channel undistortion (reader order: cv::undistort on the loaded frame, then addFrame converts)."""
+    from rd_vio_b200.frontend import FrontEnd
+    H, W = 240, 320
+    img = np.stack([random_image(H, W, seed=10 + c) for c in range(channels)], -1)
+    s = W / 752.0
+    K = np.array([[458.654 * s, 0, 367.215 * s], [0, 457.296 * s, 248.375 * H / 480.0], [0, 0, 1]], np.float32)
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+    gray = orc.bgr2gray(orc.undistort_color(img, K, D) if undistort else img)
+    with FrontEnd(W, H, max_level=2, win=21, num_slots=2, max_points=64) as fe:
+        fe.set_input_format(channels)
+        if undistort:
+            fe.set_undistort(K, D)
+        s0 = fe.acquire()
+        fe.preprocess([s0], [img])
+        assert np.array_equal(fe.download_level(s0, 0, 3), gray), "ingest (gray) frame differs"
+        assert np.array_equal(fe.download_level(s0, 0, 0), orc.clahe(gray))

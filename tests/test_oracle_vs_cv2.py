@@ -64,3 +64,19 @@ def test_undistort_vs_cv2(shape):
     K = np.array([[458.654 * s, 0, 367.215 * s], [0, 457.296 * s, 248.375 * H / 480.0], [0, 0, 1]], np.float32)
     D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
     assert np.array_equal(cv2.undistort(img, K, D), orc.undistort(img, K, D))
+
+
+def test_gray_conversion_and_color_undistort_vs_cv2():
+    import cv2
+    rng = np.random.default_rng(5)
+    H, W = 240, 320
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    bgra = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    assert np.array_equal(cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY), orc.bgr2gray(bgr))
+    assert np.array_equal(cv2.cvtColor(bgra, cv2.COLOR_BGRA2GRAY), orc.bgr2gray(bgra))
+    s = W / 752.0
+    K = np.array([[458.654 * s, 0, 367.215 * s], [0, 457.296 * s, 248.375 * H / 480.0], [0, 0, 1]], np.float32)
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+    smooth = np.stack([random_image(H, W, seed=c) for c in range(3)], -1)
+    want = cv2.cvtColor(cv2.undistort(smooth, K, D), cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(want, orc.bgr2gray(orc.undistort_color(smooth, K, D)))
