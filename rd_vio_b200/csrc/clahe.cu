@@ -203,6 +203,91 @@ clahe_apply_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int src
     }
 }
 
+// Fast path of clahe_apply_kernel for the common case (4-byte aligned sources, W % 4 == 0): identical arithmetic,
+// but every loop-invariant is hoisted, rows are walked with bumped pointers and the store takes the interior
+// branch with two integer compares.  The general kernel above stays as the fallback.
+__global__ void __launch_bounds__(256)
+clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, ClaheParams cp, ApplyBands bands,
+                        const uint8_t *__restrict__ lut, Pyramid pyr, SlotList slots) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t *comb = smem_u32;
+    const int ncx = cp.tiles_x + 1;
+    const int W = cp.W, H = cp.H, win = pyr.win;
+    float *xa_s = reinterpret_cast<float *>(comb + ncx * 256);          // [W]
+    uint32_t *cb_s = reinterpret_cast<uint32_t *>(xa_s + W);            // [W] byte offset of the cell table in comb
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int band = blockIdx.x, b = blockIdx.y;
+    const int cy = bands.cy[band], y0 = bands.y0[band], y1 = bands.y1[band];
+    const int ty1 = max(cy - 1, 0), ty2 = min(cy, cp.tiles_y - 1);
+    const uint8_t *L1 = lut + ((size_t)b * (cp.tiles_x * cp.tiles_y) + (size_t)ty1 * cp.tiles_x) * 256;
+    const uint8_t *L2 = lut + ((size_t)b * (cp.tiles_x * cp.tiles_y) + (size_t)ty2 * cp.tiles_x) * 256;
+    for (int i = tid; i < ncx * 256; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        const int o1 = max(c - 1, 0) * 256 + v, o2 = min(c, cp.tiles_x - 1) * 256 + v;
+        comb[i] = (unsigned)L1[o1] | ((unsigned)L1[o2] << 8) | ((unsigned)L2[o1] << 16) | ((unsigned)L2[o2] << 24);
+    }
+    for (int x = tid; x < W; x += 256) {
+        const float txf = (float)x * cp.inv_tw - 0.5f;
+        xa_s[x] = txf - floorf(txf);
+        int c = 0;
+        while (c < ncx - 1 && x >= cp.xb[c + 1]) ++c;
+        cb_s[x] = (uint32_t)c << 10;                                    // cell * 256 entries * 4 bytes
+    }
+    __syncthreads();
+
+    const int groups = W >> 2;
+    const int g_lo = win / 4 + 1, g_hi = (W - 5 - win) >> 2;            // interior groups: g_lo <= g <= g_hi
+    uint8_t *dst = pyr.image_origin(0, slots.v[b]);
+    const int dpitch = pyr.lv[0].ipitch;
+    const uint8_t *combb = reinterpret_cast<const uint8_t *>(comb);
+    const uint8_t *srow = src[b] + (size_t)(y0 + warp) * pitch;
+    uint8_t *drow = dst + (size_t)(y0 + warp) * dpitch;
+    for (int y = y0 + warp; y < y1; y += 8, srow += 8 * pitch, drow += 8 * (size_t)dpitch) {
+        const float tyf = (float)y * cp.inv_th - 0.5f;
+        const float ya = tyf - floorf(tyf), ya1 = 1.0f - ya;
+        const bool row_int = (y > win) && (y < H - 1 - win);
+        auto blend4 = [&](int g, unsigned px) -> unsigned {
+            const float4 xa4 = reinterpret_cast<const float4 *>(xa_s)[g];
+            const uint4 cb4 = reinterpret_cast<const uint4 *>(cb_s)[g];
+            const float xas[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
+            const unsigned cbs[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
+            unsigned rb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float xa = xas[i], xa1 = 1.0f - xa;
+                const unsigned e = *reinterpret_cast<const unsigned *>(combb + cbs[i] + 4u * __byte_perm(px, 0u, 0x4440u | (unsigned)i));
+                const float l11 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7650u)) - 8388608.0f;
+                const float l12 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7651u)) - 8388608.0f;
+                const float l21 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7652u)) - 8388608.0f;
+                const float l22 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7653u)) - 8388608.0f;
+                const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+                rb[i] = __float_as_uint(res + 12582912.0f);
+            }
+            return __byte_perm(__byte_perm(rb[0], rb[1], 0x0040u), __byte_perm(rb[2], rb[3], 0x0040u), 0x5410u);
+        };
+        const unsigned *sw = reinterpret_cast<const unsigned *>(srow);
+        unsigned *dw = reinterpret_cast<unsigned *>(drow);
+        if (row_int) {
+            // interior groups: branch-free stores, the next group's pixels are requested before this one is blended
+            int g = g_lo + lane;
+            unsigned pn = (g <= g_hi) ? __ldg(sw + g) : 0u;
+            for (; g <= g_hi; g += 32) {
+                const unsigned px = pn;
+                if (g + 32 <= g_hi) pn = __ldg(sw + g + 32);
+                dw[g] = blend4(g, px);
+            }
+            // the few groups whose mirror images live in the left / right halo
+            for (int gb = lane; gb < groups; gb += 32) {
+                if (gb >= g_lo && gb <= g_hi) { gb += ((g_hi - gb) / 32) * 32; continue; }
+                store4_border(dst, dpitch, W, H, win, gb << 2, y, blend4(gb, __ldg(sw + gb)));
+            }
+        } else {
+            for (int g = lane; g < groups; g += 32)
+                store4_border(dst, dpitch, W, H, win, g << 2, y, blend4(g, __ldg(sw + g)));
+        }
+    }
+}
+
 int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_src, size_t src_pitch,
                  int src_vec4, const ClaheParams &cp) {
     const int ntiles = cp.tiles_x * cp.tiles_y;
@@ -212,7 +297,7 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
     // row bands: split every interpolation cell row into chunks of <= RB rows
     ApplyBands bands;
     bands.nbands = 0;
-    int RB = 16;
+    int RB = 32;
     for (;;) {
         int nb = 0;
         for (int cy = 0; cy <= cp.tiles_y; ++cy) nb += (cp.yb[cy + 1] - cp.yb[cy] + RB - 1) / RB;
@@ -228,7 +313,11 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
         }
     dim3 g2(bands.nbands, slots.n);
     const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t) + (size_t)((cp.W + 3) & ~3) * 8;
-    RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_kernel<<<g2, 256, smem, ctx->ls>>>(d_src, src_pitch, src_vec4, cp, bands,
+    if (src_vec4 && cp.W % 4 == 0)
+        RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_fast_kernel<<<g2, 256, smem, ctx->ls>>>(d_src, src_pitch, cp, bands, ctx->lut,
+                                                                                              ctx->pyr, slots)));
+    else
+        RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_kernel<<<g2, 256, smem, ctx->ls>>>(d_src, src_pitch, src_vec4, cp, bands,
                                                                                          ctx->lut, ctx->pyr, slots)));
     return 2;
 }
