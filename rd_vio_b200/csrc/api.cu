@@ -278,6 +278,11 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->det.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.overflow, sizeof(unsigned)));
     CK(cudaMemset(ctx->det.overflow, 0, sizeof(unsigned)));
+    ctx->det2 = ctx->det;
+    CK(cudaMalloc(&ctx->det2.cand, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det2.cand2, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det2.cand_count, RDFE_MAX_BATCH * sizeof(unsigned)));
+    CK(cudaMalloc(&ctx->det2.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
     const size_t npts = (size_t)RDFE_MAX_BATCH * cfg->max_points;
     CK(cudaMalloc(&ctx->d_xy_a, npts * 2 * sizeof(double)));
     CK(cudaMalloc(&ctx->d_xy_b, npts * 2 * sizeof(double)));
@@ -292,6 +297,8 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     ctx->ls = ctx->stream;
     ctx->overlap = true;
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking));
@@ -337,6 +344,7 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     for (int l = 0; l < RDFE_MAX_LEVELS; ++l) { cudaFree(ctx->pyr.img[l]); cudaFree(ctx->pyr.der[l]); }
     cudaFree(ctx->raw); cudaFree(ctx->lut); cudaFree(ctx->und_map_xy); cudaFree(ctx->und_map_f); cudaFree(ctx->und_plane);
     cudaFree(ctx->det.cand); cudaFree(ctx->det.cand2); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.overflow);
+    if (ctx->det2.cand != ctx->det.cand) { cudaFree(ctx->det2.cand); cudaFree(ctx->det2.cand2); cudaFree(ctx->det2.cand_count); cudaFree(ctx->det2.frame_max); }
     cudaFree(ctx->d_xy_a); cudaFree(ctx->d_xy_b); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->d_gftt_xy); cudaFree(ctx->d_gftt_resp); cudaFree(ctx->d_gftt_counts); cudaFree(ctx->d_srcptrs);
     if (ctx->prof_ev) {
@@ -346,6 +354,8 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->aux_stream2) { cudaStreamSynchronize(ctx->aux_stream2); cudaStreamDestroy(ctx->aux_stream2); }
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->pre_stream) { cudaStreamSynchronize(ctx->pre_stream); cudaStreamDestroy(ctx->pre_stream); }
     if (ctx->ev_apply_done) cudaEventDestroy(ctx->ev_apply_done);
@@ -381,6 +391,7 @@ int rdfe_sync(rdfe_ctx *ctx) {
     if (!ctx) return RDFE_ERR_INVALID;
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream2));
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->pre_stream));
     unsigned ovf = 0;
     RDFE_CUDA_OK(cudaMemcpy(&ovf, ctx->det.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
@@ -618,14 +629,19 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     cudaEventRecord(ctx->ev_clahe_done, ps);
     cudaEventRecord(ctx->ev_apply_done, ps);
     // ---- detection branch (Harris needs only level 0): auxiliary stream
+    cudaStream_t axs = (pipe && par) ? ctx->aux_stream2 : ctx->aux_stream;
+    cudaEvent_t evj = (pipe && par) ? ctx->ev_join2 : ctx->ev_join;
+    const DetectScratch det_keep = ctx->det;
+    if (pipe && par) ctx->det = ctx->det2;           // odd steps own their candidate buffers
     if (ov) {
-        cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_apply_done, 0);
-        ctx->ls = ctx->aux_stream;
+        cudaStreamWaitEvent(axs, ctx->ev_apply_done, 0);
+        ctx->ls = axs;
     }
     rc = check_launch(ctx, launch_harris_candidates(ctx, sn, *dp, nullptr), "harris");
     if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, ctx->ls, n, *dp, gxy, gre, gcn), "select");
+    ctx->det = det_keep;
     if (rc) { restore(); return rc; }
-    if (ov) cudaEventRecord(ctx->ev_join, ctx->aux_stream);
+    if (ov) cudaEventRecord(evj, axs);
     // ---- tracking branch: pyramid levels + Scharr (still on the preprocess stream), then LK on the main stream
     ctx->ls = ps;
     rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
@@ -639,7 +655,7 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         rc = check_launch(ctx, launch_lk(ctx, spv, sn, *tp, dev_curr_xy, dev_next_xy, dev_track_counts, stride, dev_status), "lk");
         if (rc) return rc;
     }
-    if (ov) RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (ov) RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, evj, 0));
     rc = check_launch(ctx, launch_poisson_append(ctx, n, *dp, gxy, gcn, dev_next_xy, dev_kp_counts, stride), "poisson");
     if (rc) return rc;
     RDFE_CUDA_OK(cudaEventRecord(ctx->ev_step_done[par], ctx->stream));
@@ -691,6 +707,7 @@ int rdfe_set_pipelining(rdfe_ctx *ctx, int on) {
     if (!ctx) return RDFE_ERR_INVALID;
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream2));
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->pre_stream));
     ctx->pipeline_steps = on != 0;
     return RDFE_OK;

@@ -135,7 +135,9 @@ struct rdfe_ctx {
     cudaStream_t ls;              // stream the kernel launchers currently enqueue on (stream or aux_stream)
     bool overlap;                 // rdfe_frontend_step*: run Harris + selection on aux_stream beside pyramid + LK
     cudaStream_t aux_stream;      // detection branch of rdfe_frontend_step*
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t aux_stream2;     // ... of odd steps, so that Harris(t+1) may overlap select(t)
+    cudaEvent_t ev_fork, ev_join, ev_join2;
+    rdfe::DetectScratch det2;     // candidate buffers of odd steps (cand, cand2, count, max; overflow flag shared)
     // optional undistortion in front of preprocess (rdfe_set_undistort): fixed-point remap tables + output staging
     int in_channels;              // 1 gray (default), 3 BGR, 4 BGRA: cvtColor of Odometry::addFrame (rdvio.hpp:42-49)
     bool und_on;
