@@ -296,12 +296,18 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     ctx->ls = ctx->stream;
     ctx->overlap = true;
-    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&ctx->aux_stream2, cudaStreamNonBlocking));
+    // Stream priorities (0 = default/lowest, negative = higher).  The preprocessing stream of the NEXT step gets
+    // priority over the tracking/detection kernels of the current one: its short HBM-bound kernels then fill
+    // in beside the issue-bound ones instead of queueing behind their large grids (+4 % measured).
+    // RDFE_AUX_PRIO / RDFE_PRE_PRIO override for experiments.
+    const int aux_prio = getenv("RDFE_AUX_PRIO") ? atoi(getenv("RDFE_AUX_PRIO")) : 0;
+    const int pre_prio = getenv("RDFE_PRE_PRIO") ? atoi(getenv("RDFE_PRE_PRIO")) : -1;
+    CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, aux_prio));
+    CK(cudaStreamCreateWithPriority(&ctx->aux_stream2, cudaStreamNonBlocking, aux_prio));
     CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&ctx->pre_stream, cudaStreamNonBlocking, pre_prio));
     CK(cudaEventCreateWithFlags(&ctx->ev_apply_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_pre_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_step_done[0], cudaEventDisableTiming));

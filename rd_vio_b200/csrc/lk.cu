@@ -118,15 +118,28 @@ __device__ __forceinline__ Pairs load_pairs(const uint8_t *base, int o) {
     r.p3 = __funnelshift_r(b1, b2, 8);
     return r;
 }
+// Signed 16-bit weights x unsigned bytes.  The fourth Q14 weight is 2^14 minus the three rounded ones and is
+// -1 when those round up past 2^14, so the weights must be read as signed halves (the CUDA intrinsics only
+// offer same-signedness operands; PTX allows .s32.u32).
+__device__ __forceinline__ int dp2a_lo_s16_u8(unsigned w, unsigned px, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_s16_u8(unsigned w, unsigned px, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
+    return d;
+}
 // bilinear sample k (0..7) of a segment: top/bottom pair words, packed Q14 weights
 template <int K>
 __device__ __forceinline__ int sample(const Pairs &t, const Pairs &b, unsigned wt, unsigned wb) {
     const unsigned pt = (K < 4) ? ((K & 1) ? t.p1 : t.p0) : ((K & 1) ? t.p3 : t.p2);
     const unsigned pb = (K < 4) ? ((K & 1) ? b.p1 : b.p0) : ((K & 1) ? b.p3 : b.p2);
-    unsigned acc = 256u;                                  // + (1 << (W_BITS1-5-1))
-    if ((K & 2) == 0) { acc = __dp2a_lo(wt, pt, acc); acc = __dp2a_lo(wb, pb, acc); }
-    else { acc = __dp2a_hi(wt, pt, acc); acc = __dp2a_hi(wb, pb, acc); }
-    return (int)(acc >> 9);
+    int acc = 256;                                        // + (1 << (W_BITS1-5-1))
+    if ((K & 2) == 0) { acc = dp2a_lo_s16_u8(wt, pt, acc); acc = dp2a_lo_s16_u8(wb, pb, acc); }
+    else { acc = dp2a_hi_s16_u8(wt, pt, acc); acc = dp2a_hi_s16_u8(wb, pb, acc); }
+    return acc >> 9;
 }
 
 template <int WIN>
@@ -212,7 +225,7 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
         int Iyv[C::PACKED ? 1 : ROUNDS][C::PACKED ? 1 : SEG];
         int a11 = 0, a12 = 0, a22 = 0;
         {
-            const unsigned wt = (unsigned)iw00 | ((unsigned)iw01 << 16), wb = (unsigned)iw10 | ((unsigned)iw11 << 16);
+            const unsigned wt = (unsigned)iw00 | ((unsigned)iw01 << 16), wb = (unsigned)iw10 | ((unsigned)iw11 << 16);  // iw11 may be -1
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) {
                 const int o = irow[r] * JW + ioff + iseg[r] * SEG;
@@ -287,7 +300,7 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
                 cinx = inx; ciny = iny;
             }
             q14_weights(nx - (float)inx, ny - (float)iny, iw00, iw01, iw10, iw11);
-            const unsigned wt = (unsigned)iw00 | ((unsigned)iw01 << 16), wb = (unsigned)iw10 | ((unsigned)iw11 << 16);
+            const unsigned wt = (unsigned)iw00 | ((unsigned)iw01 << 16), wb = (unsigned)iw10 | ((unsigned)iw11 << 16);  // iw11 may be -1
             int b1 = 0, b2 = 0;
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) {

@@ -142,6 +142,32 @@ def test_track_parity(orc, fe752, stream0, frames0):
     assert agree >= MIN_STATUS_AGREE and err <= TOL_PX, (agree, err)
 
 
+def test_track_negative_fourth_weight(orc, fe752, stream0, frames0):
+    """Sub-pixel offsets at which the three rounded Q14 weights sum to 2^14 + 1, so the fourth is -1 (OpenCV
+    keeps it signed).  Found by a 200-frame replay: treating it as 65535 made a few points diverge."""
+    hits = [(1, 8184), (2, 4093), (3, 2728), (5, 1638), (8, 1023), (13, 630), (21, 390), (30, 273), (45, 182),
+            (63, 130), (88, 93), (90, 91), (105, 78), (117, 70)]
+    f = np.float32
+    for i, j in hits:
+        a, b = f(i) * f(2.0 ** -14), f(j) * f(2.0 ** -14)
+        w = [np.rint((f(1) - a) * (f(1) - b) * f(16384)), np.rint(a * (f(1) - b) * f(16384)), np.rint((f(1) - a) * b * f(16384))]
+        assert 16384 - sum(w) == -1
+    pre = orc.clahe(frames0[0])
+    corners, _, _ = orc.detect_keypoints(pre, np.zeros((0, 2)), 150, 20.0)
+    pts = []
+    for k, c in enumerate(corners):
+        i, j = hits[k % len(hits)]
+        if k % 2:
+            i, j = j, i
+        pts.append([c[0] + i * 2.0 ** -14, c[1] + j * 2.0 ** -14])
+    pts = np.array(pts)
+    for pred in (None, stream0.predict(0, pts)):
+        agree, err, nok, got_xy, got_st, ref_xy, ref_st = _track_case(orc, fe752, frames0[0], frames0[1], pts, pred)
+        assert nok > 100
+        assert np.array_equal(got_st, ref_st)
+        assert err == 0.0
+
+
 def test_track_large_motion_and_failures(orc, fe752, stream0, frames0):
     """Frames 3 apart with a poor guess: exercises restaging of the search region, the 0.5-px
     round-trip gate and LK failures."""

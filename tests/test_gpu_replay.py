@@ -80,7 +80,7 @@ def test_frozen_parameters_like_static_singletons(seq):
     GpuImage.reset_frozen_parameters()
 
 
-def test_cpp_plugin_replay(seq, ref, tmp_path):
+def _run_cpp_replay(seq, ref, tmp_path):
     exe = os.path.join(ROOT, "tests", "cpp", "plugin_replay")
     src = exe + ".cpp"
     lib_dir = os.path.join(ROOT, "rd_vio_b200", "lib")
@@ -106,3 +106,25 @@ def test_cpp_plugin_replay(seq, ref, tmp_path):
         i += 1 + n
         assert kp.shape == ref[fr].shape, f"frame {fr}: {kp.shape} vs {ref[fr].shape}"
         assert np.abs(kp - ref[fr]).max() <= 0.01, f"frame {fr}"
+    return r.stderr
+
+
+def test_cpp_plugin_replay(seq, ref, tmp_path):
+    _run_cpp_replay(seq, ref, tmp_path)
+
+
+def test_cpp_plugin_replay_200_frames(tmp_path):
+    """SURVEY.md 8(d) config 5 (as far as it can go without Eigen/Ceres): >= 200 frames of FeatureTracker's call
+    sequence through the C++ drop-in class, every frame's keypoints against the oracle replay; the per-frame
+    front-end latency the binary reports is written to gpurun_out/plugin_latency.txt."""
+    from rd_vio_b200.synthetic import SyntheticStream
+    st = SyntheticStream(3, 752, 480, period=200)
+    frames = [st.frame(k) for k in range(200)]
+    err = _run_cpp_replay(frames, oracle_replay(frames), tmp_path)
+    lat = [l for l in err.splitlines() if l.startswith("latency_us")]
+    assert lat, err
+    print(lat[0])
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "plugin_latency.txt"), "w") as f:
+            f.write(lat[0] + "\n")
