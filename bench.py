@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--undistort", action="store_true",
                     help="also run cv::undistort's remap in front of preprocess (SURVEY 8(f) rank 1; not the headline config)")
     ap.add_argument("--profile-steps", type=int, default=20, help="extra steps with per-kernel events")
+    ap.add_argument("--timeline", default="", help="write a per-launch timeline of 8 pipelined steps to this JSON file")
     return ap.parse_args()
 
 
@@ -201,7 +202,8 @@ def main_b200(args, wl):
     stride = 2 * NP
     # a real (non-default) stream shared by torch (copies, events) and the library (kernels): the legacy
     # default stream has handle 0, which the C ABI reads as "create your own"
-    tstream = torch.cuda.Stream()
+    # high priority: the small copies that hand each step its keypoints must not queue behind the large grids
+    tstream = torch.cuda.Stream(priority=int(os.environ.get("BENCH_MAIN_PRIO", "-1")))
     torch.cuda.set_stream(tstream)
     # three slot sets in rotation (prev, new, next-new): lets the preprocess of step t+1 overlap step t
     NSETS = 3
@@ -322,6 +324,18 @@ def main_b200(args, wl):
         for _ in range(args.profile_steps):
             step_dev(t); t += 1
         fe.sync()
+
+    if rank == 0 and args.timeline:
+        N.check(L.rdfe_profile_enable(h, 2), "profile_enable")
+        for _ in range(10):
+            step_dev(t); t += 1
+        cap = 1024
+        kid = (C.c_int * cap)(); t0s = (C.c_float * cap)(); t1s = (C.c_float * cap)(); cnt = C.c_int(0)
+        N.check(L.rdfe_profile_timeline(h, kid, t0s, t1s, cap, C.byref(cnt)), "profile_timeline")
+        N.check(L.rdfe_profile_enable(h, 0), "profile_enable")
+        with open(args.timeline, "w") as f:
+            json.dump([{"kernel": L.rdfe_profile_kernel_name(kid[i]).decode(), "start_us": round(1e3 * t0s[i], 2),
+                        "end_us": round(1e3 * t1s[i], 2)} for i in range(cnt.value)], f)
 
     # ---- end to end through the host-pointer C ABI: pinned host frames + keypoints in, results out, every step
     e2e = None

@@ -220,6 +220,9 @@ RDFE_API int rdfe_profile_num_kernels(void);
 RDFE_API const char *rdfe_profile_kernel_name(int id);
 RDFE_API int rdfe_profile_enable(rdfe_ctx *ctx, int on);
 RDFE_API int rdfe_profile_collect(rdfe_ctx *ctx, double *ms, int64_t *launches);
+/* rdfe_profile_enable(ctx, 2) keeps the streams overlapped; this returns, per launch since then, the kernel id and the
+ * stream-side start/end times in ms relative to the first launch (a timeline of the pipelined schedule). */
+RDFE_API int rdfe_profile_timeline(rdfe_ctx *ctx, int *kernel_ids, float *start_ms, float *end_ms, int cap, int *count);
 
 #ifdef __cplusplus
 }

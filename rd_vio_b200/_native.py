@@ -75,6 +75,7 @@ SYMBOLS = {
     "rdfe_profile_kernel_name": (C.c_char_p, [_i]),
     "rdfe_profile_enable": (_i, [_vp, _i]),
     "rdfe_profile_collect": (_i, [_vp, _vp, _vp]),
+    "rdfe_profile_timeline": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "rdfe_timer_start": (_i, [_vp]),
     "rdfe_timer_stop": (_i, [_vp]),
     "rdfe_timer_elapsed_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -165,6 +165,13 @@ static int stage_sources(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *
     return RDFE_OK;
 }
 
+static int sync_all_streams(rdfe_ctx *ctx) {
+    for (cudaStream_t st : {ctx->stream, ctx->aux_stream, ctx->aux_stream2, ctx->pre_stream, ctx->sel_stream[0], ctx->sel_stream[1],
+                            ctx->trk_stream, ctx->post_stream})
+        RDFE_CUDA_OK(cudaStreamSynchronize(st));
+    return RDFE_OK;
+}
+
 static int check_launch(rdfe_ctx *ctx, int launched, const char *what) {
     if (launched < 0) return launched;
     cudaError_t e = cudaGetLastError();
@@ -296,14 +303,24 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     ctx->ls = ctx->stream;
     ctx->overlap = true;
-    // Stream priorities (0 = default/lowest, negative = higher).  The preprocessing stream of the NEXT step gets
-    // priority over the tracking/detection kernels of the current one: its short HBM-bound kernels then fill
-    // in beside the issue-bound ones instead of queueing behind their large grids (+4 % measured).
-    // RDFE_AUX_PRIO / RDFE_PRE_PRIO override for experiments.
-    const int aux_prio = getenv("RDFE_AUX_PRIO") ? atoi(getenv("RDFE_AUX_PRIO")) : 0;
-    const int pre_prio = getenv("RDFE_PRE_PRIO") ? atoi(getenv("RDFE_PRE_PRIO")) : -1;
-    CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, aux_prio));
-    CK(cudaStreamCreateWithPriority(&ctx->aux_stream2, cudaStreamNonBlocking, aux_prio));
+    // Stream priorities (0 = default/lowest, negative = higher) of the pipelined step, in the order
+    // preprocess, harris, select, lk, poisson.  Kernels of equal priority are dispatched grid after grid (a
+    // large grid keeps later kernels of other streams waiting until its last CTA is placed), so the short
+    // latency-critical kernels and the upstream stages get the higher levels.  RDFE_PRIO="a,b,c,d,e" overrides.
+    int prio[5] = {-1, 0, 0, 0, 0};
+    if (const char *e = getenv("RDFE_PRIO")) sscanf(e, "%d,%d,%d,%d,%d", &prio[0], &prio[1], &prio[2], &prio[3], &prio[4]);
+    const int pre_prio = prio[0];
+    CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio[1]));
+    CK(cudaStreamCreateWithPriority(&ctx->aux_stream2, cudaStreamNonBlocking, prio[1]));
+    CK(cudaStreamCreateWithPriority(&ctx->sel_stream[0], cudaStreamNonBlocking, prio[2]));
+    CK(cudaStreamCreateWithPriority(&ctx->sel_stream[1], cudaStreamNonBlocking, prio[2]));
+    CK(cudaStreamCreateWithPriority(&ctx->trk_stream, cudaStreamNonBlocking, prio[3]));
+    CK(cudaStreamCreateWithPriority(&ctx->post_stream, cudaStreamNonBlocking, prio[4]));
+    for (int p = 0; p < 2; ++p) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_harris_done[p], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_lk_done[p], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_entry, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -318,6 +335,8 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->d_gftt_resp2, npts * sizeof(float)));
     CK(cudaMalloc(&ctx->d_gftt_counts2, RDFE_MAX_BATCH * sizeof(int)));
     ctx->last_step_slots = (uint8_t *)calloc((size_t)cfg->num_slots, 1);
+    ctx->slot_new_step = (long long *)malloc((size_t)cfg->num_slots * sizeof(long long));
+    for (int i = 0; i < cfg->num_slots; ++i) ctx->slot_new_step[i] = -16;
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_clahe_done, cudaEventDisableTiming));
     for (int p = 0; p < 2; ++p) {
@@ -361,6 +380,10 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->aux_stream2) { cudaStreamSynchronize(ctx->aux_stream2); cudaStreamDestroy(ctx->aux_stream2); }
+    for (cudaStream_t st : {ctx->sel_stream[0], ctx->sel_stream[1], ctx->trk_stream, ctx->post_stream})
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t ev : {ctx->ev_harris_done[0], ctx->ev_harris_done[1], ctx->ev_lk_done[0], ctx->ev_lk_done[1], ctx->ev_entry})
+        if (ev) cudaEventDestroy(ev);
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->pre_stream) { cudaStreamSynchronize(ctx->pre_stream); cudaStreamDestroy(ctx->pre_stream); }
@@ -381,6 +404,7 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx->slot_used);
+    free(ctx->slot_new_step);
     delete ctx;
 }
 
@@ -395,10 +419,7 @@ int rdfe_level_size(const rdfe_ctx *ctx, int level, int *width, int *height) {
 
 int rdfe_sync(rdfe_ctx *ctx) {
     if (!ctx) return RDFE_ERR_INVALID;
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream));
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream2));
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->pre_stream));
+    { const int rc_all = sync_all_streams(ctx); if (rc_all) return rc_all; }
     unsigned ovf = 0;
     RDFE_CUDA_OK(cudaMemcpy(&ovf, ctx->det.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
     if (ovf) {
@@ -605,7 +626,7 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         if ((uintptr_t)dev_images[i] % 4) vec4 = 0;
     }
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
-    const bool ov = ctx->overlap && !ctx->prof_on;                 // detection branch beside tracking branch
+    const bool ov = ctx->overlap && (!ctx->prof_on || ctx->prof_timeline);                // detection branch beside tracking branch
     const bool pipe = ov && ctx->pipeline_steps;                   // preprocess of this step beside the previous step
     const int par = (int)(ctx->step_index & 1);
     // per-step scratch alternates so that consecutive steps may overlap
@@ -614,14 +635,83 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     float *gxy = par ? ctx->d_gftt_xy2 : ctx->d_gftt_xy, *gre = par ? ctx->d_gftt_resp2 : ctx->d_gftt_resp;
     int *gcn = par ? ctx->d_gftt_counts2 : ctx->d_gftt_counts;
     if (par) { ctx->lut = ctx->lut2; ctx->d_srcptrs = ctx->d_srcptrs2; }
-    cudaStream_t ps = pipe ? ctx->pre_stream : ctx->stream;
     if (pipe) {
-        // the new slots must not be in use by the previous step; then only step s-2 has to be complete
-        bool clash = false;
+        // ---- pipelined schedule: one stream per kernel class, events for the data dependences only.
+        //   pre:    hist, apply | pyrdown, scharr          waits LK(s-2) (last reader of the slot set rewritten here)
+        //   harris: reset, harris                           waits apply(s), select(s-2) (candidate buffers of this parity)
+        //   select: select                                  waits harris(s), poisson(s-2) (gftt buffers of this parity)
+        //   track:  LK                                      waits pyramid(s), poisson(s-1) (tracked points), caller's stream
+        //   post:   poisson                                 waits LK(s), select(s); its end is the step's end
+        auto restore_p = [&]() { ctx->lut = lut_keep; ctx->d_srcptrs = src_keep; ctx->ls = ctx->stream; };
+        cudaStream_t ps = ctx->pre_stream, hs = par ? ctx->aux_stream2 : ctx->aux_stream, ss = ctx->sel_stream[par];
+        cudaStream_t ts = ctx->trk_stream, po = ctx->post_stream;
+        cudaEvent_t evj = par ? ctx->ev_join2 : ctx->ev_join;
+        bool clash = false;                               // new slots still read by the previous step?
         for (int i = 0; i < n; ++i) clash |= ctx->last_step_slots[new_slots[i]] != 0;
-        RDFE_CUDA_OK(cudaStreamWaitEvent(ps, ctx->ev_step_done[clash ? (par ^ 1) : par], 0));
+        RDFE_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+        bool renew = false;                               // ... or the NEW slots of step s-2 (Harris(s-2) read them)?
+        for (int i = 0; i < n; ++i) renew |= ctx->slot_new_step[new_slots[i]] == (long long)ctx->step_index - 2;
+        RDFE_CUDA_OK(cudaStreamWaitEvent(ps, clash ? ctx->ev_step_done[par ^ 1] : ctx->ev_lk_done[par], 0));
+        if (renew) RDFE_CUDA_OK(cudaStreamWaitEvent(ps, ctx->ev_step_done[par], 0));
         if (ctx->images_ready_valid) RDFE_CUDA_OK(cudaStreamWaitEvent(ps, ctx->images_ready, 0));
+        ctx->ls = ps;
+        const uint8_t *const *d_src = nullptr;
+        size_t spitch = 0;
+        rc = stage_sources(ctx, new_slots, n, dev_images, pitch, &d_src, &spitch, &vec4);
+        if (rc) { restore_p(); return rc; }
+        ctx->last_clahe_tiles = tiles_x * tiles_y;
+        rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), d_src, spitch, vec4, cp), "clahe");
+        if (rc) { restore_p(); return rc; }
+        cudaEventRecord(ctx->ev_clahe_done, ps);
+        cudaEventRecord(ctx->ev_apply_done, ps);
+        rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
+        if (rc) { restore_p(); return rc; }
+        cudaEventRecord(ctx->ev_pre_done, ps);
+        // detection branch
+        const DetectScratch det_keep = ctx->det;
+        if (par) ctx->det = ctx->det2;
+        cudaStreamWaitEvent(hs, ctx->ev_apply_done, 0);
+        cudaStreamWaitEvent(hs, evj, 0);                  // select(s-2) has read this parity's candidates
+        ctx->ls = hs;
+        rc = check_launch(ctx, launch_harris_candidates(ctx, sn, *dp, nullptr), "harris");
+        cudaEventRecord(ctx->ev_harris_done[par], hs);
+        if (rc == RDFE_OK) {
+            cudaStreamWaitEvent(ss, ctx->ev_harris_done[par], 0);
+            cudaStreamWaitEvent(ss, ctx->ev_step_done[par], 0);   // poisson(s-2) has read this parity's gftt output
+            ctx->ls = ss;
+            rc = check_launch(ctx, launch_gftt_select(ctx, ss, n, *dp, gxy, gre, gcn), "select");
+            cudaEventRecord(evj, ss);
+        }
+        ctx->det = det_keep;
+        if (rc) { restore_p(); return rc; }
+        // tracking branch
+        cudaStreamWaitEvent(ts, ctx->ev_entry, 0);
+        cudaStreamWaitEvent(ts, ctx->ev_pre_done, 0);
+        cudaStreamWaitEvent(ts, ctx->ev_step_done[par ^ 1], 0);
+        if (prev_slots) {
+            ctx->ls = ts;
+            rc = check_launch(ctx, launch_lk(ctx, spv, sn, *tp, dev_curr_xy, dev_next_xy, dev_track_counts, stride, dev_status), "lk");
+            if (rc) { restore_p(); return rc; }
+        }
+        cudaEventRecord(ctx->ev_lk_done[par], ts);
+        cudaStreamWaitEvent(po, ctx->ev_lk_done[par], 0);
+        cudaStreamWaitEvent(po, evj, 0);
+        ctx->ls = po;
+        rc = check_launch(ctx, launch_poisson_append(ctx, n, *dp, gxy, gcn, dev_next_xy, dev_kp_counts, stride), "poisson");
+        restore_p();
+        if (rc) return rc;
+        RDFE_CUDA_OK(cudaEventRecord(ctx->ev_step_done[par], po));
+        RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_step_done[par], 0));
+        memset(ctx->last_step_slots, 0, (size_t)ctx->cfg.num_slots);
+        for (int i = 0; i < n; ++i) {
+            ctx->last_step_slots[new_slots[i]] = 1;
+            ctx->slot_new_step[new_slots[i]] = (long long)ctx->step_index;
+            if (prev_slots) ctx->last_step_slots[prev_slots[i]] = 1;
+        }
+        ctx->step_index++;
+        return RDFE_OK;
     }
+    cudaStream_t ps = ctx->stream;
     auto restore = [&]() { ctx->lut = lut_keep; ctx->d_srcptrs = src_keep; ctx->ls = ctx->stream; };
     // ---- preprocess: CLAHE (level 0 + halo), pyramid, Scharr
     ctx->ls = ps;
@@ -635,27 +725,20 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     cudaEventRecord(ctx->ev_clahe_done, ps);
     cudaEventRecord(ctx->ev_apply_done, ps);
     // ---- detection branch (Harris needs only level 0): auxiliary stream
-    cudaStream_t axs = (pipe && par) ? ctx->aux_stream2 : ctx->aux_stream;
-    cudaEvent_t evj = (pipe && par) ? ctx->ev_join2 : ctx->ev_join;
-    const DetectScratch det_keep = ctx->det;
-    if (pipe && par) ctx->det = ctx->det2;           // odd steps own their candidate buffers
+    cudaStream_t axs = ctx->aux_stream;
+    cudaEvent_t evj = ctx->ev_join;
     if (ov) {
         cudaStreamWaitEvent(axs, ctx->ev_apply_done, 0);
         ctx->ls = axs;
     }
     rc = check_launch(ctx, launch_harris_candidates(ctx, sn, *dp, nullptr), "harris");
     if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, ctx->ls, n, *dp, gxy, gre, gcn), "select");
-    ctx->det = det_keep;
     if (rc) { restore(); return rc; }
     if (ov) cudaEventRecord(evj, axs);
     // ---- tracking branch: pyramid levels + Scharr (still on the preprocess stream), then LK on the main stream
     ctx->ls = ps;
     rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
     if (rc) { restore(); return rc; }
-    if (pipe) {
-        cudaEventRecord(ctx->ev_pre_done, ps);
-        cudaStreamWaitEvent(ctx->stream, ctx->ev_pre_done, 0);
-    }
     restore();
     if (prev_slots) {
         rc = check_launch(ctx, launch_lk(ctx, spv, sn, *tp, dev_curr_xy, dev_next_xy, dev_track_counts, stride, dev_status), "lk");
@@ -711,10 +794,7 @@ int rdfe_set_input_format(rdfe_ctx *ctx, int channels) {
 
 int rdfe_set_pipelining(rdfe_ctx *ctx, int on) {
     if (!ctx) return RDFE_ERR_INVALID;
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream));
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->aux_stream2));
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->pre_stream));
+    { const int rc_all = sync_all_streams(ctx); if (rc_all) return rc_all; }
     ctx->pipeline_steps = on != 0;
     return RDFE_OK;
 }
@@ -923,6 +1003,7 @@ int rdfe_profile_enable(rdfe_ctx *ctx, int on) {
     if (!ctx) return RDFE_ERR_INVALID;
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     ctx->prof_on = on != 0;
+    ctx->prof_timeline = on == 2;
     ctx->prof_used = 0;
     for (int k = 0; k < K_COUNT; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
     return RDFE_OK;
@@ -939,6 +1020,20 @@ int rdfe_profile_collect(rdfe_ctx *ctx, double *ms, int64_t *launches) {
     }
     ctx->prof_used = 0;
     for (int k = 0; k < K_COUNT; ++k) { ms[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_n[k]; }
+    return RDFE_OK;
+}
+
+int rdfe_profile_timeline(rdfe_ctx *ctx, int *kernel_ids, float *start_ms, float *end_ms, int cap, int *count) {
+    if (!ctx || !kernel_ids || !start_ms || !end_ms || !count) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaDeviceSynchronize());
+    const int n = ctx->prof_used < cap ? ctx->prof_used : cap;
+    for (int i = 0; i < n; ++i) {
+        kernel_ids[i] = ctx->prof_kid[i];
+        RDFE_CUDA_OK(cudaEventElapsedTime(&start_ms[i], ctx->prof_ev[0], ctx->prof_ev[2 * i]));
+        RDFE_CUDA_OK(cudaEventElapsedTime(&end_ms[i], ctx->prof_ev[0], ctx->prof_ev[2 * i + 1]));
+    }
+    *count = n;
+    ctx->prof_used = 0;
     return RDFE_OK;
 }
 

@@ -209,12 +209,16 @@ clahe_apply_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int src
 __global__ void __launch_bounds__(256)
 clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, ClaheParams cp, ApplyBands bands,
                         const uint8_t *__restrict__ lut, Pyramid pyr, SlotList slots) {
-    extern __shared__ uint32_t smem_u32[];
-    uint32_t *comb = smem_u32;
+    // shared memory: [ncx][256] float4 = the four tile-LUT values of a pixel (l11, l12, l21, l22) already as
+    // floats (one 16-byte gather per pixel, no conversions in the pixel loop), then xa, 1-xa and the cell
+    // table offset per column.
+    extern __shared__ float4 smem_f4[];
+    float4 *comb = smem_f4;
     const int ncx = cp.tiles_x + 1;
     const int W = cp.W, H = cp.H, win = pyr.win;
     float *xa_s = reinterpret_cast<float *>(comb + ncx * 256);          // [W]
-    uint32_t *cb_s = reinterpret_cast<uint32_t *>(xa_s + W);            // [W] byte offset of the cell table in comb
+    float *xa1_s = xa_s + W;                                            // [W]
+    uint32_t *cb_s = reinterpret_cast<uint32_t *>(xa1_s + W);           // [W] byte offset of the cell table in comb
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int band = blockIdx.x, b = blockIdx.y;
     const int cy = bands.cy[band], y0 = bands.y0[band], y1 = bands.y1[band];
@@ -224,14 +228,16 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
     for (int i = tid; i < ncx * 256; i += 256) {
         const int c = i >> 8, v = i & 255;
         const int o1 = max(c - 1, 0) * 256 + v, o2 = min(c, cp.tiles_x - 1) * 256 + v;
-        comb[i] = (unsigned)L1[o1] | ((unsigned)L1[o2] << 8) | ((unsigned)L2[o1] << 16) | ((unsigned)L2[o2] << 24);
+        comb[i] = make_float4(u8_to_float(L1[o1]), u8_to_float(L1[o2]), u8_to_float(L2[o1]), u8_to_float(L2[o2]));
     }
     for (int x = tid; x < W; x += 256) {
         const float txf = (float)x * cp.inv_tw - 0.5f;
-        xa_s[x] = txf - floorf(txf);
+        const float xa = txf - floorf(txf);
+        xa_s[x] = xa;
+        xa1_s[x] = 1.0f - xa;
         int c = 0;
         while (c < ncx - 1 && x >= cp.xb[c + 1]) ++c;
-        cb_s[x] = (uint32_t)c << 10;                                    // cell * 256 entries * 4 bytes
+        cb_s[x] = (uint32_t)c << 12;                                    // cell * 256 entries * 16 bytes
     }
     __syncthreads();
 
@@ -248,19 +254,17 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
         const bool row_int = (y > win) && (y < H - 1 - win);
         auto blend4 = [&](int g, unsigned px) -> unsigned {
             const float4 xa4 = reinterpret_cast<const float4 *>(xa_s)[g];
+            const float4 xb4 = reinterpret_cast<const float4 *>(xa1_s)[g];
             const uint4 cb4 = reinterpret_cast<const uint4 *>(cb_s)[g];
             const float xas[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
+            const float xbs[4] = {xb4.x, xb4.y, xb4.z, xb4.w};
             const unsigned cbs[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
             unsigned rb[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float xa = xas[i], xa1 = 1.0f - xa;
-                const unsigned e = *reinterpret_cast<const unsigned *>(combb + cbs[i] + 4u * __byte_perm(px, 0u, 0x4440u | (unsigned)i));
-                const float l11 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7650u)) - 8388608.0f;
-                const float l12 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7651u)) - 8388608.0f;
-                const float l21 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7652u)) - 8388608.0f;
-                const float l22 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7653u)) - 8388608.0f;
-                const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+                const float xa = xas[i], xa1 = xbs[i];
+                const float4 e = *reinterpret_cast<const float4 *>(combb + cbs[i] + 16u * __byte_perm(px, 0u, 0x4440u | (unsigned)i));
+                const float res = (e.x * xa1 + e.y * xa) * ya1 + (e.z * xa1 + e.w * xa) * ya;
                 rb[i] = __float_as_uint(res + 12582912.0f);
             }
             return __byte_perm(__byte_perm(rb[0], rb[1], 0x0040u), __byte_perm(rb[2], rb[3], 0x0040u), 0x5410u);
@@ -281,9 +285,26 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
                 if (gb >= g_lo && gb <= g_hi) { gb += ((g_hi - gb) / 32) * 32; continue; }
                 store4_border(dst, dpitch, W, H, win, gb << 2, y, blend4(gb, __ldg(sw + gb)));
             }
-        } else {
+        } else if (H - 1 - win <= win) {
+            // tiny image: a row may have mirror images in both halos
             for (int g = lane; g < groups; g += 32)
                 store4_border(dst, dpitch, W, H, win, g << 2, y, blend4(g, __ldg(sw + g)));
+        } else {
+            // a row whose mirror image lies in the top / bottom halo: interior column groups store the same word
+            // twice (row y and its REFLECT_101 image), only the side groups take the general path
+            ptrdiff_t mirror = 0;
+            if (y >= 1 && y <= win) mirror = -2 * (ptrdiff_t)y * dpitch;
+            else if (y >= H - 1 - win && y <= H - 2) mirror = 2 * (ptrdiff_t)(H - 1 - y) * dpitch;
+            unsigned *dm = reinterpret_cast<unsigned *>(drow + mirror);
+            for (int g = g_lo + lane; g <= g_hi; g += 32) {
+                const unsigned v = blend4(g, __ldg(sw + g));
+                dw[g] = v;
+                if (mirror) dm[g] = v;
+            }
+            for (int gb = lane; gb < groups; gb += 32) {
+                if (gb >= g_lo && gb <= g_hi) { gb += ((g_hi - gb) / 32) * 32; continue; }
+                store4_border(dst, dpitch, W, H, win, gb << 2, y, blend4(gb, __ldg(sw + gb)));
+            }
         }
     }
 }
@@ -313,10 +334,19 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
         }
     dim3 g2(bands.nbands, slots.n);
     const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t) + (size_t)((cp.W + 3) & ~3) * 8;
-    if (src_vec4 && cp.W % 4 == 0)
-        RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_fast_kernel<<<g2, 256, smem, ctx->ls>>>(d_src, src_pitch, cp, bands, ctx->lut,
-                                                                                              ctx->pyr, slots)));
-    else
+    const size_t smem_fast = (size_t)(cp.tiles_x + 1) * 256 * sizeof(float4) + (size_t)cp.W * 12;
+    if (src_vec4 && cp.W % 4 == 0 && smem_fast <= 100 * 1024) {
+        static size_t s_attr = 0;
+        if (smem_fast > 48 * 1024 && smem_fast > s_attr) {
+            if (cudaFuncSetAttribute(clahe_apply_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast) != cudaSuccess) {
+                set_error("clahe: cudaFuncSetAttribute(%zu) failed", smem_fast);
+                return RDFE_ERR_CUDA;
+            }
+            s_attr = smem_fast;
+        }
+        RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_fast_kernel<<<g2, 256, smem_fast, ctx->ls>>>(d_src, src_pitch, cp, bands, ctx->lut,
+                                                                                                   ctx->pyr, slots)));
+    } else
         RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_kernel<<<g2, 256, smem, ctx->ls>>>(d_src, src_pitch, src_vec4, cp, bands,
                                                                                          ctx->lut, ctx->pyr, slots)));
     return 2;

@@ -137,6 +137,10 @@ struct rdfe_ctx {
     cudaStream_t aux_stream;      // detection branch of rdfe_frontend_step*
     cudaStream_t aux_stream2;     // ... of odd steps, so that Harris(t+1) may overlap select(t)
     cudaEvent_t ev_fork, ev_join, ev_join2;
+    // pipelined rdfe_frontend_step*: every kernel class on its own stream (and priority), linked by events
+    cudaStream_t sel_stream[2], trk_stream, post_stream;
+    cudaEvent_t ev_harris_done[2], ev_lk_done[2], ev_entry;
+    long long *slot_new_step;     // [num_slots] step index at which the slot was last a step's NEW slot
     rdfe::DetectScratch det2;     // candidate buffers of odd steps (cand, cand2, count, max; overflow flag shared)
     // optional undistortion in front of preprocess (rdfe_set_undistort): fixed-point remap tables + output staging
     int in_channels;              // 1 gray (default), 3 BGR, 4 BGRA: cvtColor of Odometry::addFrame (rdvio.hpp:42-49)
@@ -183,6 +187,7 @@ struct rdfe_ctx {
     int last_clahe_tiles;
     // optional per-kernel CUDA-event timing (rdfe_profile_*)
     bool prof_on;
+    bool prof_timeline;           // events recorded without serialising the streams (rdfe_profile_enable(ctx, 2))
     int prof_used;
     cudaEvent_t *prof_ev;         // [2 * kProfMax]
     int prof_kid[rdfe::kProfMax];

@@ -19,6 +19,7 @@ namespace rdfe {
 
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_CAP = 2048;
+constexpr int SEL_WIN = 8;           // greedy window: words of 32 sorted candidates tested per round
 
 struct SelectParams {
     int W, H;
@@ -143,6 +144,7 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
         if (n_el > SEL_CAP) {
             if (tid == 0) { s_prefix = 0; s_k = SEL_CAP; }
             unsigned long long mask = 0;
+            bool early = false;
             for (int pass = 7; pass >= 0; --pass) {
                 if (pass < 4 && pass >= low_passes) continue;      // digits known to be zero
                 const int shift = pass * 8;
@@ -195,8 +197,12 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
                 }
                 mask |= 255ull << shift;
                 __syncthreads();
+                // The response bits are settled after pass 4.  Any threshold gives an exact batch (a prefix of the
+                // sorted order), so unless ties on the response leave the batch less than half full, take the
+                // keys whose response is strictly larger and skip the address passes.
+                if (pass == 4 && SEL_CAP - s_k >= SEL_CAP / 2) { early = true; break; }
             }
-            lo = s_prefix;
+            lo = early ? s_prefix + (1ull << 32) : s_prefix;
         }
         // ---- gather [lo, hi) and sort descending
         if (tid == 0) s_nb = 0;
@@ -214,23 +220,60 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
         while (N < nb) N <<= 1;
         for (unsigned i = nb + tid; i < N; i += SEL_THREADS) batch[i] = 0ull;
         __syncthreads();
-        for (unsigned k2 = 2; k2 <= N; k2 <<= 1) {
-            for (unsigned j = k2 >> 1; j > 0; j >>= 1) {
-                for (unsigned t = tid; t < (N >> 1); t += SEL_THREADS) {
-                    const unsigned i = 2 * j * (t / j) + (t % j);
-                    const unsigned p = i + j;
-                    const unsigned long long a = batch[i], c = batch[p];
-                    const bool desc = ((i & k2) == 0);
-                    if (desc ? (a < c) : (a > c)) { batch[i] = c; batch[p] = a; }
+        // Bitonic sort, descending.  Thread t owns elements 2t and 2t+1 for the exchange distances j <= 32 (its
+        // partner for distance j is lane t ^ (j/2): register shuffles, no barrier); distances >= 64 go through
+        // shared memory.  All merges up to k2 = 64 stay inside one warp's 64 elements.
+        {
+            const unsigned half = N >> 1;
+            const bool warp_on = (unsigned)(warp * 32) < half;            // warp-uniform
+            const bool own = (unsigned)tid < half;
+            const unsigned e_idx = 2u * (unsigned)tid;
+            unsigned long long e0 = 0ull, e1 = 0ull;
+            auto reg_stages = [&](unsigned k2, unsigned jstart) {
+                const bool desc = (e_idx & k2) == 0;
+                for (unsigned j = jstart; j >= 2; j >>= 1) {
+                    const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, e0, (int)(j >> 1));
+                    const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, e1, (int)(j >> 1));
+                    const bool keep_max = ((e_idx & j) == 0) == desc;
+                    e0 = keep_max ? (e0 > p0 ? e0 : p0) : (e0 < p0 ? e0 : p0);
+                    e1 = keep_max ? (e1 > p1 ? e1 : p1) : (e1 < p1 ? e1 : p1);
+                }
+                const unsigned long long hi = e0 > e1 ? e0 : e1, lo = e0 > e1 ? e1 : e0;
+                e0 = desc ? hi : lo;
+                e1 = desc ? lo : hi;
+            };
+            if (warp_on) {
+                if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
+                for (unsigned k2 = 2; k2 <= min(N, 64u); k2 <<= 1) reg_stages(k2, k2 >> 1);
+                if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
+            }
+            __syncthreads();
+            for (unsigned k2 = 128; k2 <= N; k2 <<= 1) {
+                for (unsigned j = k2 >> 1, lj = 31 - __clz(k2 >> 1); j >= 64; j >>= 1, --lj) {
+                    if (own) {
+                        const unsigned t = (unsigned)tid;
+                        const unsigned i = ((t >> lj) << (lj + 1)) | (t & (j - 1u));
+                        const unsigned q = i + j;
+                        const unsigned long long a = batch[i], c = batch[q];
+                        const bool desc = ((i & k2) == 0);
+                        if (desc ? (a < c) : (a > c)) { batch[i] = c; batch[q] = a; }
+                    }
+                    __syncthreads();
+                }
+                if (warp_on) {
+                    if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
+                    reg_stages(k2, 32u);
+                    if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
                 }
                 __syncthreads();
             }
         }
-        // ---- greedy acceptance, in rounds.  Round: (1) ALL warps test the not-yet-visited candidates of the
-        // sorted batch against the accepted-corner grid in parallel (a candidate that fails is dead for good:
-        // the accepted set only grows); (2) warp 0 takes the first 32 survivors IN ORDER, resolves the order
-        // dependence among them lane by lane (exactly the sequential greedy) and inserts the winners.
-        // Survivors beyond those 32 are re-tested in the next round against the enlarged grid.
+        // ---- greedy acceptance, in rounds.  Round: (1) the next SEL_WIN words (32 candidates each) of the sorted
+        // batch are tested against the accepted-corner grid, one warp per word (a candidate that fails is dead
+        // for good: the accepted set only grows); (2) warp 0 takes the first 32 survivors of that window IN
+        // ORDER, resolves the order dependence among them lane by lane (exactly the sequential greedy) and
+        // inserts the winners.  Survivors beyond those 32 are re-tested in the next round against the enlarged
+        // grid; candidates beyond the window are not touched until the window reaches them.
         {
             constexpr int NMASK = SEL_CAP / 32;
             __shared__ unsigned s_mask[NMASK];
@@ -247,7 +290,8 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
                 const int nacc_r = s_naccepted;
                 if (pos0 >= nb || nacc_r >= sp.max_corners) break;
                 // (1) re-test the alive, not yet visited candidates against the grown grid
-                for (unsigned wv = (pos0 >> 5) + warp; wv < NMASK; wv += SEL_THREADS / 32) {
+                const unsigned w0 = pos0 >> 5, wend = min(w0 + (unsigned)SEL_WIN, (unsigned)NMASK);
+                for (unsigned wv = w0 + warp; wv < wend; wv += SEL_THREADS / 32) {
                     const unsigned alive = s_mask[wv];
                     if (alive == 0u) continue;                                  // warp-uniform
                     const unsigned idx = wv * 32 + lane;
@@ -265,11 +309,10 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
                     // lane r picks the r-th survivor (in batch order)
                     unsigned c0 = 0, c1 = 0;
                     // words entirely below pos0 are history; the word containing pos0 was re-masked above (idx >= pos0)
-                    const unsigned w0 = pos0 >> 5;
                     if (NMASK > 32) {
-                        c0 = ((unsigned)lane >= w0) ? __popc(s_mask[lane]) : 0u;
-                        c1 = ((unsigned)lane + 32u >= w0) ? __popc(s_mask[lane + 32]) : 0u;
-                    } else if (lane < NMASK) c0 = ((unsigned)lane >= w0) ? __popc(s_mask[lane]) : 0u;
+                        c0 = ((unsigned)lane >= w0 && (unsigned)lane < wend) ? __popc(s_mask[lane]) : 0u;
+                        c1 = ((unsigned)lane + 32u >= w0 && (unsigned)lane + 32u < wend) ? __popc(s_mask[lane + 32]) : 0u;
+                    } else if (lane < NMASK) c0 = ((unsigned)lane >= w0 && (unsigned)lane < wend) ? __popc(s_mask[lane]) : 0u;
                     unsigned inc0 = c0, inc1 = c1;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -282,7 +325,7 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
                     const unsigned r = (unsigned)lane;
                     int widx = -1;
                     unsigned before = 0;
-                    for (int wq = 0; wq < NMASK; ++wq) {     // warp-uniform shuffles; 64 inclusive counts live across lanes
+                    for (int wq = (int)w0; wq < (int)wend; ++wq) {     // warp-uniform shuffles; 64 inclusive counts live across lanes
                         const unsigned incw = (wq < 32) ? __shfl_sync(0xffffffffu, inc0, wq & 31) : __shfl_sync(0xffffffffu, inc1, wq & 31);
                         const unsigned cw = (wq < 32) ? __shfl_sync(0xffffffffu, c0, wq & 31) : __shfl_sync(0xffffffffu, c1, wq & 31);
                         if (widx < 0 && r < total && incw > r) { widx = wq; before = incw - cw; }
@@ -332,7 +375,7 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
                     const unsigned last_idx = __shfl_sync(0xffffffffu, idx, (int)max(taken, 1u) - 1);
                     if (lane == 0) {
                         s_naccepted = nacc;
-                        s_pos = (total <= 32u) ? nb : last_idx + 1;
+                        s_pos = (total <= 32u) ? min(wend * 32u, nb) : last_idx + 1;    // window exhausted, or resume after the last one taken
                     }
                 }
                 __syncthreads();

@@ -55,6 +55,24 @@ def test_track_vs_cv2(stream0, frames0):
         assert ok.sum() > 100 and np.abs(n_cv[ok] - n_or[ok]).max() <= 0.01
 
 
+def test_track_negative_fourth_weight_vs_cv2(stream0, frames0):
+    """Sub-pixel offsets whose three rounded Q14 bilinear weights sum to 2^14 + 1: OpenCV keeps the fourth
+    weight (-1) signed, and so must the restatement (and the CUDA kernel, tests/test_gpu_parity.py)."""
+    hits = [(1, 8184), (2, 4093), (3, 2728), (5, 1638), (8, 1023), (13, 630), (21, 390), (30, 273), (45, 182),
+            (63, 130), (88, 93), (90, 91), (105, 78), (117, 70)]
+    A, B = Cv2Image(frames0[0]), Cv2Image(frames0[1])
+    A.preprocess(); B.preprocess()
+    corners = orc.detect_keypoints(A.image, np.zeros((0, 2)), 150, 20.0)[0]
+    pts = np.array([[c[0] + hits[k % len(hits)][k % 2] * 2.0 ** -14, c[1] + hits[k % len(hits)][1 - k % 2] * 2.0 ** -14]
+                    for k, c in enumerate(corners)])
+    PA, PB = orc.Pyramid(A.image), orc.Pyramid(B.image)
+    n_cv, s_cv = A.track_keypoints(B, pts, None)
+    n_or, s_or, _ = orc.track_keypoints(PA, PB, pts, None)
+    assert np.array_equal(s_cv != 0, s_or != 0)
+    ok = s_cv != 0
+    assert ok.sum() > 100 and np.abs(n_cv[ok] - n_or[ok]).max() <= 0.01
+
+
 @pytest.mark.parametrize("shape", [(480, 752), (720, 1280), (257, 331)])
 def test_undistort_vs_cv2(shape):
     import cv2
