@@ -23,40 +23,56 @@ constexpr int kHistWarps = 8;
 __global__ void __launch_bounds__(kHistWarps * 32)
 clahe_hist_lut_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int vec4, ClaheParams cp,
                       uint8_t *__restrict__ lut) {
-    __shared__ unsigned hist[kHistWarps][256];
+    // per-warp private histograms; bins 256..511 of each are trash bins for the bytes of an edge word that lie
+    // outside the tile (keeps the atomics branch-free; never zeroed, never read)
+    // The rows must start at a multiple of 2048 in the shared address space (the atomics below compose
+    // "row base | trash bit | 4 * byte" with an OR); the static base is not (the first KB of the window is
+    // reserved), so one spare row is allocated and the base rounded up at run time.
+    __shared__ __align__(16) unsigned hist_raw[(kHistWarps + 1) * 512];
     __shared__ unsigned wsum[kHistWarps];
+    const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist_raw);
+    unsigned (*hist)[512] = reinterpret_cast<unsigned (*)[512]>(hist_raw + ((((hist_sa + 2047u) & ~2047u) - hist_sa) >> 2));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, b = blockIdx.y;
     const int tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
     const uint8_t *img = src[b];
 
-    for (int i = tid; i < kHistWarps * 256; i += kHistWarps * 32) (&hist[0][0])[i] = 0u;
+    for (int i = tid; i < kHistWarps * 64; i += kHistWarps * 32) reinterpret_cast<uint4 *>(&hist[i >> 6][0])[i & 63] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
 
     const int x0 = tx * cp.tw, y0 = ty * cp.th;
     if (!cp.padded && vec4) {
-        // aligned 32-bit words covering the tile row; bytes outside [x0, x0+tw) are masked.  All the row
-        // loads of a warp are issued before the first atomic so that they overlap (the kernel is latency-bound).
+        // aligned 32-bit words covering the tile row.  All the row loads of a warp are issued before the first
+        // atomic so that they overlap (the kernel is latency-bound).
         const int wa = x0 & ~3;                                    // first aligned column
         const int nwords = ((x0 + cp.tw + 3) & ~3) - wa >> 2;     // words per row
         constexpr int RPW = 8;                                     // rows per warp batch
+        unsigned *hw = hist[warp];
         for (int yb = warp * RPW; yb < cp.th; yb += kHistWarps * RPW) {
             for (int wi = lane; wi < nwords; wi += 32) {
                 unsigned wv[RPW];
+                const uint8_t *rp = img + (size_t)(y0 + yb) * pitch + wa + 4 * wi;
 #pragma unroll
-                for (int r = 0; r < RPW; ++r) {
-                    const int y = yb + r;
-                    wv[r] = (y < cp.th) ? __ldg(reinterpret_cast<const unsigned *>(img + (size_t)(y0 + y) * pitch + wa) + wi) : 0u;
-                }
+                for (int r = 0; r < RPW; ++r, rp += pitch)
+                    wv[r] = (yb + r < cp.th) ? __ldg(reinterpret_cast<const unsigned *>(rp)) : 0u;
                 const int xw = wa + 4 * wi;
+                // bytes of this lane's word column outside [x0, x0 + tw) go to the trash half (byte offset 1024);
+                // the same for every row
+                // (hist rows are 2048-byte aligned, so row base | trash bit | 4 * byte is a plain OR)
+                unsigned t4[4];
+                const unsigned hb = (unsigned)__cvta_generic_to_shared(hw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t4[k] = hb | (((xw + k >= x0) && (xw + k < x0 + cp.tw)) ? 0u : 1024u);
+                auto bump = [](unsigned addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); };
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
-                    if (yb + r < cp.th) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int x = xw + k;
-                            if (x >= x0 && x < x0 + cp.tw) atomicAdd(&hist[warp][(wv[r] >> (8 * k)) & 255u], 1u);
-                        }
+                    if (yb + r < cp.th) {                          // warp-uniform
+                        const unsigned w = wv[r];
+                        // byte offset of the bin = 4 * byte, extracted pre-scaled
+                        bump(((w << 2) & 0x3FCu) | t4[0]);
+                        bump(((w >> 6) & 0x3FCu) | t4[1]);
+                        bump(((w >> 14) & 0x3FCu) | t4[2]);
+                        bump(((w >> 22) & 0x3FCu) | t4[3]);
                     }
                 }
             }

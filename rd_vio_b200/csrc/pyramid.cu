@@ -43,54 +43,52 @@ pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items) {
     const bool ld_ok = (sx + 7 <= gs.w + pyr.win - 1);       // also the first inactive lane: its taps feed lane-1
     const bool edge_l = (lane == 0), edge_r = (lane == 31);
 
-    int h0[4], h1[4], h2[4], h3[4];                          // horizontal sums of input rows y-4 .. y-1
-#pragma unroll
-    for (int k = 0; k < 4; ++k) h0[k] = h1[k] = h2[k] = h3[k] = 0;
+    // Two outputs per 32-bit register (16-bit fields): h*01 = outputs 0 and 1 of the lane, h*23 = outputs 2, 3.
+    // Horizontal sums are <= 16 * 255, the vertical sum + 128 <= 65408: every field stays within 16 bits, so the
+    // packed adds/multiplies never carry across fields (bit-exact).
+    unsigned h0a = 0, h1a = 0, h2a = 0, h3a = 0, h0b = 0, h1b = 0, h2b = 0, h3b = 0;   // input rows y-4 .. y-1
 
     const int ystart = 2 * i0 - 2, nsteps = 2 * rows + 3;    // input rows 2*i0-2 .. 2*(i0+rows-1)+2
-    // software pipelining: the words of step s+1 are requested before step s is consumed
+    // software pipelining: the words of step s+1 are requested before step s is consumed.  The read after the
+    // last step is input row 2*(i0+rows)+1 <= h+2: inside the halo (win >= 3 rows), so it needs no guard.
     const bool el = edge_l && active, er = edge_r && active && (sx + 8 <= gs.w + pyr.win - 4);
-    auto load_row = [&](int y, uint2 &w, unsigned &xl, unsigned &xr) {
-        const uint8_t *row = src + (ptrdiff_t)y * gs.ipitch;
+    const uint8_t *row = src + (ptrdiff_t)ystart * gs.ipitch + sx;
+    auto load_row = [&](uint2 &w, unsigned &xl, unsigned &xr) {
         w = make_uint2(0u, 0u);
         xl = 0u; xr = 0u;
-        if (ld_ok) w = *reinterpret_cast<const uint2 *>(row + sx);
-        if (el) xl = *reinterpret_cast<const unsigned *>(row + sx - 4);
-        if (er) xr = *reinterpret_cast<const unsigned *>(row + sx + 8);
+        if (ld_ok) w = *reinterpret_cast<const uint2 *>(row);
+        if (el) xl = *reinterpret_cast<const unsigned *>(row - 4);
+        if (er) xr = *reinterpret_cast<const unsigned *>(row + 8);
+        row += gs.ipitch;
     };
     uint2 wn; unsigned xln, xrn;
-    load_row(ystart, wn, xln, xrn);
+    load_row(wn, xln, xrn);
     for (int s = 0; s < nsteps; ++s) {
         const uint2 w = wn;
         const unsigned xl = xln, xr = xrn;
-        if (s + 1 < nsteps) load_row(ystart + s + 1, wn, xln, xrn);
+        load_row(wn, xln, xrn);
         unsigned wl = __shfl_up_sync(0xffffffffu, w.y, 1);   // columns sx-4 .. sx-1
         unsigned wr = __shfl_down_sync(0xffffffffu, w.x, 1); // columns sx+8 .. sx+11
         if (el) wl = xl;
         if (er) wr = xr;
-        // taps: p[-2..8] relative to sx
-        unsigned p[11];
-        p[0] = bfe8(wl, 2); p[1] = bfe8(wl, 3);
-        p[2] = bfe8(w.x, 0); p[3] = bfe8(w.x, 1); p[4] = bfe8(w.x, 2); p[5] = bfe8(w.x, 3);
-        p[6] = bfe8(w.y, 0); p[7] = bfe8(w.y, 1); p[8] = bfe8(w.y, 2); p[9] = bfe8(w.y, 3);
-        p[10] = bfe8(wr, 0);
-        int hn[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            hn[k] = (int)(p[2 * k] + p[2 * k + 4] + 4u * (p[2 * k + 1] + p[2 * k + 3]) + 6u * p[2 * k + 2]);
+        // taps p[-2..8] relative to sx: p0 p1 = wl bytes 2 3, p2..p5 = w.x, p6..p9 = w.y, p10 = wr byte 0
+        const unsigned Ex = w.x & 0x00FF00FFu, Ox = __byte_perm(w.x, 0u, 0x4341u);   // (p2,p4) (p3,p5)
+        const unsigned Ey = w.y & 0x00FF00FFu, Oy = __byte_perm(w.y, 0u, 0x4341u);   // (p6,p8) (p7,p9)
+        const unsigned p02 = __byte_perm(wl, Ex, 0x5452u), p13 = __byte_perm(wl, Ox, 0x5453u);
+        const unsigned p46 = __byte_perm(Ex, Ey, 0x5432u), p57 = __byte_perm(Ox, Oy, 0x5432u);
+        const unsigned p8a = __byte_perm(Ey, wr, 0x3432u);                           // (p8,p10)
+        const unsigned hna = p02 + p46 + 4u * (p13 + Ox) + 6u * Ex;                  // outputs 0, 1
+        const unsigned hnb = p46 + p8a + 4u * (p57 + Oy) + 6u * Ey;                  // outputs 2, 3
         if (s >= 4 && (s & 1) == 0) {
             // input row y = 2i+2  =>  output row i = (y-2)/2
             const int i = i0 + ((s - 4) >> 1);
-            unsigned out = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int v = h0[k] + hn[k] + 4 * (h1[k] + h3[k]) + 6 * h2[k];
-                out |= (unsigned)((v + 128) >> 8) << (8 * k);
-            }
+            const unsigned va = h0a + hna + 4u * (h1a + h3a) + 6u * h2a + 0x00800080u;
+            const unsigned vb = h0b + hnb + 4u * (h1b + h3b) + 6u * h2b + 0x00800080u;
+            const unsigned out = __byte_perm(va, vb, 0x7531u);                       // (v + 128) >> 8 of each field
             if (active) store4_with_halo(dst, gd.ipitch, gd.w, gd.h, pyr.win, j0, i, out);
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { h0[k] = h1[k]; h1[k] = h2[k]; h2[k] = h3[k]; h3[k] = hn[k]; }
+        h0a = h1a; h1a = h2a; h2a = h3a; h3a = hna;
+        h0b = h1b; h1b = h2b; h2b = h3b; h3b = hnb;
     }
 }
 
@@ -122,8 +120,14 @@ scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
     const uint8_t *rp = pyr.image_origin(l, slot) + (ptrdiff_t)(y0 - 1) * ipitch + c0;     // row y0-1
     uint8_t *op = reinterpret_cast<uint8_t *>(pyr.deriv_origin(l, slot)) + (size_t)y0 * dpitch + 4 * (size_t)c0;
 
-    // rows y-2, y-1: p(x+1)-p(x-1) and 3p(x-1)+10p(x)+3p(x+1)
-    int d1A[4] = {0, 0, 0, 0}, d1B[4] = {0, 0, 0, 0}, s2A[4] = {0, 0, 0, 0}, s2B[4] = {0, 0, 0, 0};
+    // Two pixels per 32-bit register (16-bit fields): A-registers hold the lane's pixels 0 and 2, B-registers
+    // pixels 1 and 3.  Per row and pixel: d = p(x+1) - p(x-1) kept with a bias of 2048 (so the vertical 3/10/3
+    // sum carries 16 * 2048 = 2^15 and never leaves its field), s = 3p(x-1) + 10p(x) + 3p(x+1) <= 4080.
+    // dx = 3(d[y-1] + d[y+1]) + 10 d[y], dy = s[y+1] - s[y-1] + 2^15; flipping bit 15 of a field removes the bias
+    // without carries and leaves the int16 two's complement value.  All fields stay within 16 bits, so the packed
+    // 32-bit adds/multiplies never carry across fields: bit-exact.
+    constexpr unsigned BD = 0x08000800u, B15 = 0x80008000u;
+    unsigned dA0 = 0, dA1 = 0, dB0 = 0, dB1 = 0, sA0 = 0, sA1 = 0, sB0 = 0, sB1 = 0;   // rows y-2 (…0) and y-1 (…1)
     unsigned wn = 0, xln = 0, xrn = 0;
     if (ld_ok) wn = *reinterpret_cast<const unsigned *>(rp);
     if (el) xln = *reinterpret_cast<const unsigned *>(rp - 4);
@@ -133,43 +137,38 @@ scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
     for (int s = 0; s < nsteps; ++s) {
         const unsigned w = wn, xl = xln, xr = xrn;
         rp += ipitch;
-        if (s + 1 < nsteps) {                                 // software pipelining: next row in flight
-            if (ld_ok) wn = *reinterpret_cast<const unsigned *>(rp);
-            if (el) xln = *reinterpret_cast<const unsigned *>(rp - 4);
-            if (er) xrn = *reinterpret_cast<const unsigned *>(rp + 4);
-        }
+        // software pipelining: next row in flight.  After the last step this reads row y0 + rows + 1 <= h + 1,
+        // which lies inside the halo (win >= 2 rows): no guard needed.
+        if (ld_ok) wn = *reinterpret_cast<const unsigned *>(rp);
+        if (el) xln = *reinterpret_cast<const unsigned *>(rp - 4);
+        if (er) xrn = *reinterpret_cast<const unsigned *>(rp + 4);
         unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
         if (el) wl = xl;
         if (er) wr = xr;
-        int p[6];
-        p[0] = (int)(wl >> 24);
-        p[1] = (int)(w & 0xFFu); p[2] = (int)__byte_perm(w, 0u, 0x4441u); p[3] = (int)__byte_perm(w, 0u, 0x4442u); p[4] = (int)(w >> 24);
-        p[5] = (int)(wr & 0xFFu);
-        int d1N[4], s2N[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            d1N[k] = p[k + 2] - p[k];
-            s2N[k] = 3 * (p[k] + p[k + 2]) + 10 * p[k + 1];
-        }
+        const unsigned A = w & 0x00FF00FFu;                    // (v0, v2)
+        const unsigned B = __byte_perm(w, 0u, 0x4341u);        // (v1, v3)
+        const unsigned LA = __byte_perm(wl, B, 0x5453u);       // (vL, v1): left neighbours of A
+        const unsigned RB = __byte_perm(A, wr, 0x3432u);       // (v2, vR): right neighbours of B
+        const unsigned dAn = B + BD - LA, dBn = RB + BD - A;
+        const unsigned sAn = 3u * (LA + B) + 10u * A, sBn = 3u * (A + RB) + 10u * B;
         if (s >= 2) {
-            unsigned o[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int gx = 3 * (d1A[k] + d1N[k]) + 10 * d1B[k];
-                const int gy = s2N[k] - s2A[k];
-                o[k] = __byte_perm((unsigned)gx, (unsigned)gy, 0x5410u);      // (dx, dy) int16 pair
-            }
+            const unsigned xa = (3u * (dA0 + dAn) + 10u * dA1) ^ B15, xb = (3u * (dB0 + dBn) + 10u * dB1) ^ B15;
+            const unsigned ya = (sAn + B15 - sA0) ^ B15, yb = (sBn + B15 - sB0) ^ B15;
+            // (dx, dy) int16 pairs of pixels 0..3
+            const unsigned o0 = __byte_perm(xa, ya, 0x5410u), o2 = __byte_perm(xa, ya, 0x7632u);
+            const unsigned o1 = __byte_perm(xb, yb, 0x5410u), o3 = __byte_perm(xb, yb, 0x7632u);
             if (full) {
-                *reinterpret_cast<uint4 *>(op) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4 *>(op) = make_uint4(o0, o1, o2, o3);
             } else if (active) {
+                const unsigned o[4] = {o0, o1, o2, o3};
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (c0 + k < gw) reinterpret_cast<unsigned *>(op)[k] = o[k];
             }
             op += dpitch;
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { d1A[k] = d1B[k]; d1B[k] = d1N[k]; s2A[k] = s2B[k]; s2B[k] = s2N[k]; }
+        dA0 = dA1; dA1 = dAn; dB0 = dB1; dB1 = dBn;
+        sA0 = sA1; sA1 = sAn; sB0 = sB1; sB1 = sBn;
     }
 }
 
