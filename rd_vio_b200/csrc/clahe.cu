@@ -258,6 +258,8 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
     __syncthreads();
 
     const int groups = W >> 2;
+    const bool coop = coop_halo_ok(W, win);
+    const int nh = (win + 3) >> 2;
     const int g_lo = win / 4 + 1, g_hi = (W - 5 - win) >> 2;            // interior groups: g_lo <= g <= g_hi
     uint8_t *dst = pyr.image_origin(0, slots.v[b]);
     const int dpitch = pyr.lv[0].ipitch;
@@ -287,7 +289,21 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
         };
         const unsigned *sw = reinterpret_cast<const unsigned *>(srow);
         unsigned *dw = reinterpret_cast<unsigned *>(drow);
-        if (row_int) {
+        if (coop) {
+            // all groups of the row in batches of 32; the first / last batch also writes the side halos from
+            // registers (store4_row_coop), rows next to the top / bottom edge are stored twice
+            const int last = ((groups - 1) >> 5) << 5;
+            unsigned pn = (lane < groups) ? __ldg(sw + lane) : 0u;
+            for (int gbase = 0; gbase < groups; gbase += 32) {
+                const int g = gbase + lane;
+                const bool act = g < groups;
+                const unsigned px = pn;
+                if (g + 32 < groups) pn = __ldg(sw + g + 32);
+                const unsigned v = blend4(act ? g : groups - 1, px);
+                if (row_int) store4_row_coop(drow, W, nh, g, act, v, gbase == 0, gbase == last);
+                else store4_rows_coop(dst, dpitch, W, H, win, nh, g, y, act, v, gbase == 0, gbase == last);
+            }
+        } else if (row_int) {
             // interior groups: branch-free stores, the next group's pixels are requested before this one is blended
             int g = g_lo + lane;
             unsigned pn = (g <= g_hi) ? __ldg(sw + g) : 0u;

@@ -81,6 +81,38 @@ __device__ __forceinline__ void store4_border(uint8_t *org, int pitch, int W, in
     if (y >= 1 && y <= win) store4_row(org - (ptrdiff_t)y * pitch, W, win, x, nvalid, v4, near_x);
     if (y >= H - 1 - win && y <= H - 2) store4_row(org + (ptrdiff_t)(2 * (H - 1) - y) * pitch, W, win, x, nvalid, v4, near_x);
 }
+// Warp-cooperative store of one image row in 4-pixel groups, REFLECT_101 side halos included.  Lane owns group g
+// (columns 4g .. 4g+3, value v) or is inactive; ALL 32 lanes must call, with consecutive g across the lanes.
+// `left` / `right` (warp-uniform): this batch of 32 groups holds the nh = ceil(win / 4) groups next to the left /
+// right image edge and one more neighbour (checked by the caller, together with W % 4 == 0).  The halo is written as
+// aligned words assembled from the lane's own group and its neighbour's (one shuffle + one PRMT + one store per
+// side) instead of byte by byte; up to 3 columns beyond `win` are filled too (still the correct mirror values).
+__device__ __forceinline__ void store4_row_coop(uint8_t *row, int W, int nh, int g, bool active, unsigned v,
+                                                bool left, bool right) {
+    if (active) *reinterpret_cast<unsigned *>(row + 4 * g) = v;
+    if (left) {
+        const unsigned nx = __shfl_down_sync(0xffffffffu, v, 1);
+        // columns -4(g+1) .. -4g-1 mirror columns 4g+4, 4g+3, 4g+2, 4g+1
+        if (active && g < nh) *reinterpret_cast<unsigned *>(row - 4 * (g + 1)) = __byte_perm(v, nx, 0x1234u);
+    }
+    if (right) {
+        const unsigned pv = __shfl_up_sync(0xffffffffu, v, 1);
+        const int m = (W >> 2) - 1 - g;      // columns W+4m .. W+4m+3 mirror columns W-2-4m, W-3-4m, W-4-4m, W-5-4m
+        if (active && m < nh) *reinterpret_cast<unsigned *>(row + W + 4 * m) = __byte_perm(v, pv, 0x7012u);
+    }
+}
+// ... and its mirror images in the top / bottom halo (y warp-uniform)
+__device__ __forceinline__ void store4_rows_coop(uint8_t *org, int pitch, int W, int H, int win, int nh, int g, int y,
+                                                 bool active, unsigned v, bool left, bool right) {
+    store4_row_coop(org + (ptrdiff_t)y * pitch, W, nh, g, active, v, left, right);
+    if (y >= 1 && y <= win) store4_row_coop(org - (ptrdiff_t)y * pitch, W, nh, g, active, v, left, right);
+    if (y >= H - 1 - win && y <= H - 2) store4_row_coop(org + (ptrdiff_t)(2 * (H - 1) - y) * pitch, W, nh, g, active, v, left, right);
+}
+// whether store4_row(s)_coop applies to rows of W pixels cut into batches of 32 groups
+__host__ __device__ __forceinline__ bool coop_halo_ok(int W, int win) {
+    const int G = W >> 2, nh = (win + 3) >> 2;
+    return (W & 3) == 0 && G >= nh + 1 && (G - 1 - nh) / 32 == (G - 1) / 32;
+}
 __device__ __forceinline__ void store4_with_halo(uint8_t *org, int pitch, int W, int H, int win, int x, int y,
                                                  unsigned v4) {
     // interior: no mirror image of these pixels lies in the halo (small levels may have no interior at all)

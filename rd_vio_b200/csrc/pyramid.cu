@@ -8,7 +8,7 @@
 //                    lacks from lane+-1 by shuffle, keeps the horizontal sums of the last 5 input rows
 //                    in registers and emits one output row every second step as a 4-byte store
 //                    (128 B per warp).  The producer also writes the output level's win-px
-//                    REFLECT_101 halo (store4_with_halo), so no separate halo pass exists.
+//                    REFLECT_101 halo (store4_rows_coop / store4_with_halo), so no separate halo pass exists.
 //   scharr_kernel    all levels in one launch, same rolling scheme (4 pixels per lane, 3-row window):
 //                    un-normalised 3x3 Scharr, (dx,dy) int16 pairs, one 16-byte store per lane per row.
 // Both read their border taps from the materialised REFLECT_101 halo of the source level -- exactly the
@@ -42,6 +42,10 @@ pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items) {
     // input columns sx-2 .. sx+8 are needed; all inside [-2, w+1] for active lanes (halo >= 2 px)
     const bool ld_ok = (sx + 7 <= gs.w + pyr.win - 1);       // also the first inactive lane: its taps feed lane-1
     const bool edge_l = (lane == 0), edge_r = (lane == 31);
+    // halo of the output level: warp-cooperative word stores when the row geometry allows it
+    const bool coop = coop_halo_ok(gd.w, pyr.win);
+    const int nh = (pyr.win + 3) >> 2;
+    const bool tile_l = (item % tiles_x) == 0, tile_r = (item % tiles_x) == tiles_x - 1;
 
     // Two outputs per 32-bit register (16-bit fields): h*01 = outputs 0 and 1 of the lane, h*23 = outputs 2, 3.
     // Horizontal sums are <= 16 * 255, the vertical sum + 128 <= 65408: every field stays within 16 bits, so the
@@ -85,7 +89,8 @@ pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items) {
             const unsigned va = h0a + hna + 4u * (h1a + h3a) + 6u * h2a + 0x00800080u;
             const unsigned vb = h0b + hnb + 4u * (h1b + h3b) + 6u * h2b + 0x00800080u;
             const unsigned out = __byte_perm(va, vb, 0x7531u);                       // (v + 128) >> 8 of each field
-            if (active) store4_with_halo(dst, gd.ipitch, gd.w, gd.h, pyr.win, j0, i, out);
+            if (coop) store4_rows_coop(dst, gd.ipitch, gd.w, gd.h, pyr.win, nh, j0 >> 2, i, active, out, tile_l, tile_r);
+            else if (active) store4_with_halo(dst, gd.ipitch, gd.w, gd.h, pyr.win, j0, i, out);
         }
         h0a = h1a; h1a = h2a; h2a = h3a; h3a = hna;
         h0b = h1b; h1b = h2b; h2b = h3b; h3b = hnb;
