@@ -172,6 +172,35 @@ static int sync_all_streams(rdfe_ctx *ctx) {
     return RDFE_OK;
 }
 
+// Host frames -> the upload staging of their slots.  When the host pointers and the slots are both equally spaced
+// (a batch cut out of per-stream ring buffers, consecutive slots) all frames go in ONE 2-D copy (one "row" per
+// frame) instead of n calls: the per-call overhead of 64 small copies costs more than the PCIe time.
+static int upload_frames(rdfe_ctx *ctx, cudaStream_t st, const int *slots, int n, const uint8_t *const *images, size_t pitch,
+                         std::vector<const uint8_t *> &dptr) {
+    const size_t row_bytes = (size_t)ctx->cfg.width * ctx->in_channels;
+    const size_t frame_bytes = pitch * (size_t)ctx->cfg.height;
+    for (int i = 0; i < n; ++i) dptr[i] = ctx->raw + (size_t)slots[i] * ctx->raw_slot;
+    bool strided = n > 1 && pitch == ctx->raw_pitch;
+    const ptrdiff_t hstep = n > 1 ? images[1] - images[0] : 0;
+    const int sstep = n > 1 ? slots[1] - slots[0] : 0;
+    if (strided && (hstep < (ptrdiff_t)frame_bytes || sstep < 1)) strided = false;
+    for (int i = 2; strided && i < n; ++i)
+        if (images[i] - images[i - 1] != hstep || slots[i] - slots[i - 1] != sstep) strided = false;
+    if (strided) {
+        RDFE_CUDA_OK(cudaMemcpy2DAsync(const_cast<uint8_t *>(dptr[0]), (size_t)sstep * ctx->raw_slot, images[0], (size_t)hstep,
+                                       frame_bytes, (size_t)n, cudaMemcpyHostToDevice, st));
+        return RDFE_OK;
+    }
+    for (int i = 0; i < n; ++i) {
+        uint8_t *d = const_cast<uint8_t *>(dptr[i]);
+        if (pitch == ctx->raw_pitch)
+            RDFE_CUDA_OK(cudaMemcpyAsync(d, images[i], frame_bytes, cudaMemcpyHostToDevice, st));
+        else
+            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, row_bytes, (size_t)ctx->cfg.height, cudaMemcpyHostToDevice, st));
+    }
+    return RDFE_OK;
+}
+
 static int check_launch(rdfe_ctx *ctx, int launched, const char *what) {
     if (launched < 0) return launched;
     cudaError_t e = cudaGetLastError();
@@ -480,16 +509,10 @@ int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n, const uint8_t 
     if (!images || pitch < (size_t)ctx->cfg.width * ctx->in_channels) { set_error("rdfe_preprocess_batch: bad image pointers/pitch"); return RDFE_ERR_INVALID; }
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
     std::vector<const uint8_t *> dptr(n);
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i)
         if (!images[i]) { set_error("rdfe_preprocess_batch: image %d is null", i); return RDFE_ERR_INVALID; }
-        uint8_t *d = ctx->raw + (size_t)slots[i] * ctx->raw_slot;
-        if (pitch == ctx->raw_pitch)
-            RDFE_CUDA_OK(cudaMemcpyAsync(d, images[i], pitch * (size_t)ctx->cfg.height, cudaMemcpyHostToDevice, ctx->stream));
-        else
-            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width * ctx->in_channels, (size_t)ctx->cfg.height,
-                                           cudaMemcpyHostToDevice, ctx->stream));
-        dptr[i] = d;
-    }
+    rc = upload_frames(ctx, ctx->stream, slots, n, images, pitch, dptr);
+    if (rc) return rc;
     rc = rdfe_preprocess_batch_dev(ctx, slots, n, dptr.data(), ctx->raw_pitch, clip_limit, tiles_x, tiles_y);
     if (rc) return rc;
     return rdfe_sync(ctx);
@@ -828,14 +851,9 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
     RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_clahe_done, 0));     // last reader of the raw staging
     RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[p], 0));        // stage buffers free again
     std::vector<const uint8_t *> dptr(n);
-    for (int i = 0; i < n; ++i) {
-        uint8_t *d = ctx->raw + (size_t)new_slots[i] * ctx->raw_slot;
-        if (pitch == ctx->raw_pitch)
-            RDFE_CUDA_OK(cudaMemcpyAsync(d, images[i], pitch * (size_t)ctx->cfg.height, cudaMemcpyHostToDevice, ctx->copy_stream));
-        else
-            RDFE_CUDA_OK(cudaMemcpy2DAsync(d, ctx->raw_pitch, images[i], pitch, (size_t)ctx->cfg.width * ctx->in_channels, (size_t)ctx->cfg.height,
-                                           cudaMemcpyHostToDevice, ctx->copy_stream));
-        dptr[i] = d;
+    {
+        const int rc_up = upload_frames(ctx, ctx->copy_stream, new_slots, n, images, pitch, dptr);
+        if (rc_up) return rc_up;
     }
     rdfe_track_params tpl;
     if (tp) tpl = *tp; else rdfe_default_track_params(&tpl);
