@@ -138,6 +138,16 @@ struct ClaheParams {
     int yb[kMaxTiles + 2];
 };
 
+// Strip height of the warp-rolling kernels: `max_rows` at full batches; smaller (never below `min_rows`) when the
+// batch is too small to give every SM a few warps -- a strip is walked row by row, so its height is the kernel's
+// latency in the single-stream plugin path.  warps_per_row_strip = column tiles * images.
+inline int adaptive_strip_rows(int height, int warps_per_row_strip, int min_rows, int max_rows) {
+    const int want_warps = 148 * 8;
+    int rows = (int)(((long long)height * warps_per_row_strip + want_warps - 1) / want_warps);
+    rows = (rows + 3) & ~3;
+    return rows < min_rows ? min_rows : rows > max_rows ? max_rows : rows;
+}
+
 enum KernelId {
     K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_COUNT
 };

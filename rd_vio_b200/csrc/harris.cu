@@ -31,7 +31,7 @@ namespace rdfe {
 //   * the 3-tap row smoothing ((k0*p[x-1]) + k1*p[x]) + k0*p[x+1] is not associative, so on the
 //     mirrored columns x = -1 and x = W it is evaluated in mirrored order.
 // All float64 sums are exact (9 terms, exponent spread < 2^29), hence order independent.
-constexpr int HR_ROWS = 44;            // output rows per warp strip
+constexpr int HR_ROWS = 44;            // output rows per warp strip at full batches (adaptive_strip_rows)
 constexpr int HR_COLS = 120;           // output columns per warp (lanes 1..30)
 constexpr int HW_WARPS = 4;            // warps per CTA
 constexpr int HW_BUF = 256;            // per-warp candidate staging (keys)
@@ -60,7 +60,7 @@ __device__ __forceinline__ double shfl_down_d(double v) {
 // One strip (HR_ROWS x 120 outputs) by one warp.  BORDER = false is the lean variant for strips whose
 // whole 128-column x (rows+6)-row footprint lies inside the image: no mirror/sign/validity logic at all.
 template <bool kFma, bool BORDER>
-__device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0, float k,
+__device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0, int hr_rows, float k,
                                              const DetectScratch &det, int b, float *__restrict__ response,
                                              unsigned long long *buf, unsigned *cnt) {
     const int lane = threadIdx.x & 31;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
         __syncwarp();
     };
 
-    const int rows = min(HR_ROWS, H - y0);
+    const int rows = min(hr_rows, H - y0);
     const int steps = rows + 6;
     // software pipelining: the pixel words of rows j+1, j+2 are in flight while row j is processed
     const uint8_t *rowp = org + (ptrdiff_t)(y0 - 3) * ipitch + c0;
@@ -235,7 +235,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
 template <bool kFma>
 __global__ void __launch_bounds__(HW_WARPS * 32)
 harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
-                  int n_items) {
+                  int n_items, int hr_rows) {
     __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
     __shared__ unsigned s_cnt[HW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -243,15 +243,15 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
     if (item >= n_items) return;
     const int b = blockIdx.y, slot = slots.v[b];
     const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
-    const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * HR_ROWS;
+    const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * hr_rows;
     const uint8_t *org = pyr.image_origin(0, slot);
     if (lane == 0) s_cnt[warp] = 0u;
     __syncwarp();
     // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+HR_ROWS+2 all inside the image, and the
     // outputs stay off the 1-px frame
-    const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + HR_ROWS + 2 < H);
-    if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, k, det, b, response, s_buf[warp], &s_cnt[warp]);
-    else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+    const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
+    if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+    else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
 }
 
 __global__ void detect_reset_kernel(DetectScratch det, int n) {
@@ -262,13 +262,15 @@ __global__ void detect_reset_kernel(DetectScratch det, int n) {
 int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_response) {
     const LevelGeom &g = ctx->pyr.lv[0];
     detect_reset_kernel<<<1, RDFE_MAX_BATCH, 0, ctx->ls>>>(ctx->det, slots.n);
-    const int tiles_x = (g.w + HR_COLS - 1) / HR_COLS, strips = (g.h + HR_ROWS - 1) / HR_ROWS;
+    const int tiles_x = (g.w + HR_COLS - 1) / HR_COLS;
+    const int hr_rows = adaptive_strip_rows(g.h, tiles_x * slots.n, 8, HR_ROWS);
+    const int strips = (g.h + hr_rows - 1) / hr_rows;
     const int n_items = tiles_x * strips;
     dim3 grid((n_items + HW_WARPS - 1) / HW_WARPS, slots.n);
     if (p.harris_fma)
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items, hr_rows)));
     else
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items, hr_rows)));
     return 2;
 }
 

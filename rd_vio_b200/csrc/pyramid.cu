@@ -23,10 +23,10 @@ constexpr int PW_WARPS = 4;            // warps per CTA (independent strips)
 __device__ __forceinline__ unsigned bfe8(unsigned w, int k) { return (w >> (8 * k)) & 0xFFu; }
 
 // ---------------------------------------------------------------- pyrDown
-constexpr int PD_ROWS = 8;             // output rows per warp strip
+constexpr int PD_ROWS = 8;             // output rows per warp strip at full batches (adaptive_strip_rows)
 
 __global__ void __launch_bounds__(PW_WARPS * 32)
-pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items) {
+pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items, int pd_rows) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = blockIdx.x * PW_WARPS + warp;
     if (item >= n_items) return;
@@ -35,8 +35,8 @@ pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items) {
     const uint8_t *src = pyr.image_origin(l, slot);
     uint8_t *dst = pyr.image_origin(l + 1, slot);
     const int j0 = (item % tiles_x) * 128 + 4 * lane;       // first of this lane's 4 output columns
-    const int i0 = (item / tiles_x) * PD_ROWS;              // first output row of the strip
-    const int rows = min(PD_ROWS, gd.h - i0);
+    const int i0 = (item / tiles_x) * pd_rows;              // first output row of the strip
+    const int rows = min(pd_rows, gd.h - i0);
     const int sx = 2 * j0;                                   // input column of this lane's 8-byte word
     const bool active = j0 < gd.w;
     // input columns sx-2 .. sx+8 are needed; all inside [-2, w+1] for active lanes (halo >= 2 px)
@@ -98,11 +98,12 @@ pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items) {
 }
 
 // ----------------------------------------------------------------- Scharr
-constexpr int SC_ROWS = 16;            // output rows per warp strip
+constexpr int SC_ROWS = 16;            // output rows per warp strip at full batches (adaptive_strip_rows)
 
 struct ItemTable {
-    int first[RDFE_MAX_LEVELS + 1];   // first flattened work item of each level
+    int first[RDFE_MAX_LEVELS + 1];   // work items (warps) of each level
     int tiles_x[RDFE_MAX_LEVELS];
+    int rows[RDFE_MAX_LEVELS];        // strip height of each level
 };
 
 __global__ void __launch_bounds__(PW_WARPS * 32)
@@ -116,8 +117,8 @@ scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
     const int gw = pyr.lv[l].w, gh = pyr.lv[l].h, ipitch = pyr.lv[l].ipitch, dpitch = pyr.lv[l].dpitch;
     const int tiles_x = tt.tiles_x[l];
     const int c0 = (item % tiles_x) * 128 + 4 * lane;
-    const int y0 = (item / tiles_x) * SC_ROWS;
-    const int rows = min(SC_ROWS, gh - y0);
+    const int y0 = (item / tiles_x) * tt.rows[l];
+    const int rows = min(tt.rows[l], gh - y0);
     const bool active = c0 < gw;
     const bool ld_ok = (c0 + 3 <= gw + pyr.win - 1);          // inside the halo (also the first inactive lane)
     const bool el = (lane == 0) && active, er = (lane == 31) && active;
@@ -182,10 +183,12 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
     int launches = 0;
     for (int l = 0; l + 1 < pyr.nlevels; ++l) {
         const LevelGeom &gd = pyr.lv[l + 1];
-        const int tiles_x = (gd.w + 127) / 128, strips = (gd.h + PD_ROWS - 1) / PD_ROWS;
+        const int tiles_x = (gd.w + 127) / 128;
+        const int pd_rows = adaptive_strip_rows(gd.h, tiles_x * slots.n, 2, PD_ROWS);
+        const int strips = (gd.h + pd_rows - 1) / pd_rows;
         const int n_items = tiles_x * strips;
         dim3 grid((n_items + PW_WARPS - 1) / PW_WARPS, slots.n);
-        RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, l, tiles_x, n_items)));
+        RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, l, tiles_x, n_items, pd_rows)));
         ++launches;
     }
     ItemTable tt;
@@ -193,7 +196,8 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
     for (int l = 0; l < pyr.nlevels; ++l) {
         const LevelGeom &g = pyr.lv[l];
         tt.tiles_x[l] = (g.w + 127) / 128;
-        tt.first[l] = tt.tiles_x[l] * ((g.h + SC_ROWS - 1) / SC_ROWS);      // work items (warps) of level l
+        tt.rows[l] = adaptive_strip_rows(g.h, tt.tiles_x[l] * slots.n, 4, SC_ROWS);
+        tt.first[l] = tt.tiles_x[l] * ((g.h + tt.rows[l] - 1) / tt.rows[l]);      // work items (warps) of level l
         max_items = tt.first[l] > max_items ? tt.first[l] : max_items;
     }
     RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3((max_items + PW_WARPS - 1) / PW_WARPS, slots.n, pyr.nlevels), PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, tt)));
