@@ -59,6 +59,10 @@ class GpuFrontEnd {
         if (rdfe_create(&cfg, &ctx) != RDFE_OK) {
             std::fprintf(stderr, "rdvio GpuImage: %s\n", rdfe_last_error());
             ctx = nullptr;
+        } else {
+            // preprocess() returns once the frame is uploaded: the image Mat outlives the copy (it is held until
+            // release_image_buffer()), and track/detect are ordered behind the pyramid on the context's stream
+            rdfe_set_host_sync(ctx, 0);
         }
         ctxs[key] = ctx;
         return ctx;
@@ -66,6 +70,19 @@ class GpuFrontEnd {
     static int &device() {
         static int dev = 0;
         return dev;
+    }
+    // OpenCvImage::gftt is a function-local static created by the first detect_keypoints call of the process
+    // (opencv_image.cpp:184-188): its max_points is frozen there.  0 = not called yet.
+    static size_t &frozen_max_points() {
+        static size_t v = 0;
+        return v;
+    }
+    static rdfe_detect_params detect_params(size_t frozen) {
+        rdfe_detect_params p;
+        rdfe_default_detect_params(&p);
+        p.max_points = (int)(frozen ? frozen : 4096);
+        if (p.max_points > 2048) p.max_points = 2048;
+        return p;
     }
 };
 
@@ -93,19 +110,26 @@ class GpuImage : public Image {
         if (!ctx_) return;
         if (slot_ < 0 && rdfe_slot_acquire(ctx_, &slot_) != RDFE_OK) { slot_ = -1; return; }
         const uint8_t *src = image.data;
-        if (rdfe_preprocess_batch(ctx_, &slot_, 1, &src, (size_t)image.step, s_clip, s_w, s_h) != RDFE_OK)
+        if (rdfe_preprocess_batch(ctx_, &slot_, 1, &src, (size_t)image.step, s_clip, s_w, s_h) != RDFE_OK) {
             std::fprintf(stderr, "rdvio GpuImage::preprocess: %s\n", rdfe_last_error());
+            return;
+        }
+        // FeatureTracker calls track(prev -> this) and then detect(this) (feature_tracker.cpp:43-96).  Corner
+        // selection needs neither the tracked points nor the pyramid levels above 0, so once the detector's
+        // parameters are frozen it is started here and runs beside the tracking call.
+        if (const size_t frozen = GpuFrontEnd::frozen_max_points()) {
+            const rdfe_detect_params p = GpuFrontEnd::detect_params(frozen);
+            rdfe_detect_prefetch(ctx_, &slot_, 1, &p);      // optional: a failure only means detect does the work itself
+        }
     }
 
     void detect_keypoints(std::vector<vector<2>> &keypoints, size_t max_points = 1000,
                           double keypoint_distance = 10) const override {
         // static singleton semantics of OpenCvImage::gftt (opencv_image.cpp:184-188)
-        static const size_t s_max_points = max_points;
+        size_t &frozen = GpuFrontEnd::frozen_max_points();
+        if (frozen == 0) frozen = max_points ? max_points : 4096;
         if (!ctx_ || slot_ < 0) return;
-        rdfe_detect_params p;
-        rdfe_default_detect_params(&p);
-        p.max_points = (int)(s_max_points ? s_max_points : 4096);
-        if (p.max_points > 2048) p.max_points = 2048;
+        rdfe_detect_params p = GpuFrontEnd::detect_params(frozen);
         p.keypoint_distance = keypoint_distance;
         int count = (int)keypoints.size();
         const int stride = count + p.max_points;

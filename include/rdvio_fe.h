@@ -133,6 +133,18 @@ RDFE_API int rdfe_detect_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const
                           float *dev_gftt_xy, float *dev_gftt_resp, int *dev_gftt_counts);
 
 /* ---- OpenCvImage::track_keypoints (opencv_image.cpp:75-154) ------------- */
+/* Optional: start Harris + GFTT selection for these (already preprocessed) slots on an internal stream.  They need
+ * only level 0 of the image and none of the tracked points, so they can run while rdfe_track_batch works.  A later
+ * rdfe_detect_batch[_dev] on exactly these slots with the same GFTT parameters (max_points, quality_level,
+ * min_distance, harris_k, harris_fma) and no GFTT taps then only runs the Poisson append; any other call pattern
+ * simply ignores the prefetch.  Results are identical with or without it. */
+RDFE_API int rdfe_detect_prefetch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p);
+
+/* Host-pointer rdfe_preprocess_batch: on (default) = returns when the pyramid is complete; off = returns as soon as
+ * the uploads are issued (pageable memory: already staged; pinned memory: the caller keeps the frames alive until
+ * the next synchronising call).  Later calls are ordered behind it on the context's stream either way. */
+RDFE_API int rdfe_set_host_sync(rdfe_ctx *ctx, int on);
+
 /* Forward pyramidal LK curr->next, border/jump gating, backward LK, 0.5-px
  * round-trip gate, all in one launch.  curr_xy, next_xy: [n][stride][2]
  * doubles; counts[i] points for image i; status: [n][stride] chars in {0,1}.

@@ -76,6 +76,8 @@ SYMBOLS = {
     "rdfe_profile_enable": (_i, [_vp, _i]),
     "rdfe_profile_collect": (_i, [_vp, _vp, _vp]),
     "rdfe_profile_timeline": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "rdfe_detect_prefetch": (_i, [_vp, _vp, _i, _vp]),
+    "rdfe_set_host_sync": (_i, [_vp, _i]),
     "rdfe_timer_start": (_i, [_vp]),
     "rdfe_timer_stop": (_i, [_vp]),
     "rdfe_timer_elapsed_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -364,6 +364,13 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->d_gftt_resp2, npts * sizeof(float)));
     CK(cudaMalloc(&ctx->d_gftt_counts2, RDFE_MAX_BATCH * sizeof(int)));
     ctx->last_step_slots = (uint8_t *)calloc((size_t)cfg->num_slots, 1);
+    CK(cudaEventCreateWithFlags(&ctx->pf_done, cudaEventDisableTiming));
+    CK(cudaMalloc(&ctx->pf_gftt_xy, npts * 2 * sizeof(float)));
+    CK(cudaMalloc(&ctx->pf_gftt_resp, npts * sizeof(float)));
+    CK(cudaMalloc(&ctx->pf_gftt_counts, RDFE_MAX_BATCH * sizeof(int)));
+    CK(cudaMallocHost(&ctx->h_overflow, sizeof(unsigned)));
+    *ctx->h_overflow = 0u;
+    ctx->host_sync = true;
     ctx->slot_new_step = (long long *)malloc((size_t)cfg->num_slots * sizeof(long long));
     for (int i = 0; i < cfg->num_slots; ++i) ctx->slot_new_step[i] = -16;
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -432,6 +439,9 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->pf_done) cudaEventDestroy(ctx->pf_done);
+    cudaFree(ctx->pf_gftt_xy); cudaFree(ctx->pf_gftt_resp); cudaFree(ctx->pf_gftt_counts);
+    if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
     free(ctx->slot_used);
     free(ctx->slot_new_step);
     delete ctx;
@@ -476,6 +486,8 @@ int rdfe_slot_release(rdfe_ctx *ctx, int slot) {
         return RDFE_ERR_INVALID;
     }
     ctx->slot_used[slot] = 0;
+    for (int i = 0; ctx->pf_valid && i < ctx->pf_n; ++i)
+        if (ctx->pf_slots[i] == slot) ctx->pf_valid = false;
     return RDFE_OK;
 }
 
@@ -490,6 +502,10 @@ int rdfe_preprocess_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const uint
     rc = make_clahe_params(ctx, clip_limit, tiles_x, tiles_y, &cp);
     if (rc) return rc;
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->pf_recorded) RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->pf_done, 0));   // a prefetch may still read these slots
+    for (int i = 0; ctx->pf_valid && i < ctx->pf_n; ++i)
+        for (int j = 0; j < n; ++j)
+            if (ctx->pf_slots[i] == slots[j]) ctx->pf_valid = false;
     const uint8_t *const *d_src = nullptr;
     size_t spitch = 0;
     int vec4 = 0;
@@ -515,10 +531,23 @@ int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n, const uint8_t 
     if (rc) return rc;
     rc = rdfe_preprocess_batch_dev(ctx, slots, n, dptr.data(), ctx->raw_pitch, clip_limit, tiles_x, tiles_y);
     if (rc) return rc;
-    return rdfe_sync(ctx);
+    if (!ctx->host_sync) return RDFE_OK;          // rdfe_set_host_sync(ctx, 0): results are consumed in stream order
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return RDFE_OK;
 }
 
 // ----------------------------------------------------------------- detect
+// a prefetch is usable when it covers exactly these slots with the same GFTT parameters (the Poisson radius and the
+// border only matter to the append stage, which always runs in the detect call itself)
+static bool prefetch_matches(const rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p) {
+    if (n != ctx->pf_n) return false;
+    for (int i = 0; i < n; ++i)
+        if (slots[i] != ctx->pf_slots[i]) return false;
+    const rdfe_detect_params &q = ctx->pf_params;
+    return p->max_points == q.max_points && p->quality_level == q.quality_level && p->min_distance == q.min_distance &&
+           p->harris_k == q.harris_k && p->harris_fma == q.harris_fma;
+}
+
 static int check_detect(const rdfe_ctx *ctx, const rdfe_detect_params *p, int stride, const char *what) {
     if (!p || p->max_points < 1 || p->max_points > ctx->cfg.max_points || stride < 1) {
         set_error("%s: max_points=%d (capacity %d) stride=%d invalid", what, p ? p->max_points : -1, ctx->cfg.max_points, stride);
@@ -539,10 +568,50 @@ int rdfe_detect_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const rdfe_det
     rc = check_detect(ctx, p, stride, "rdfe_detect_batch_dev");
     if (rc) return rc;
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->pf_valid && !dev_gftt_xy && !dev_gftt_resp && !dev_gftt_counts && prefetch_matches(ctx, slots, n, p)) {
+        // Harris + GFTT selection of exactly these slots already ran (or still run) on the prefetch stream
+        ctx->pf_valid = false;
+        RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->pf_done, 0));
+        return check_launch(ctx, launch_poisson_append(ctx, n, *p, ctx->pf_gftt_xy, ctx->pf_gftt_counts, dev_keypoints_xy,
+                                                       dev_counts, stride), "poisson");
+    }
     rc = check_launch(ctx, launch_harris_candidates(ctx, sl, *p, nullptr), "harris");
     if (rc) return rc;
     return check_launch(ctx, launch_select(ctx, sl, *p, dev_keypoints_xy, dev_counts, stride, dev_gftt_xy, dev_gftt_resp,
                                            dev_gftt_counts), "select");
+}
+
+int rdfe_detect_prefetch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p) {
+    SlotList sl;
+    int rc = check_slots(ctx, slots, n, &sl, "rdfe_detect_prefetch");
+    if (rc) return rc;
+    rc = check_detect(ctx, p, 1, "rdfe_detect_prefetch");
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t ax = ctx->aux_stream2;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));          // level 0 of the slots is produced on the main stream
+    RDFE_CUDA_OK(cudaStreamWaitEvent(ax, ctx->ev_fork, 0));
+    const DetectScratch det_keep = ctx->det;
+    ctx->det = ctx->det2;
+    ctx->ls = ax;
+    rc = check_launch(ctx, launch_harris_candidates(ctx, sl, *p, nullptr), "harris");
+    if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, ax, n, *p, ctx->pf_gftt_xy, ctx->pf_gftt_resp, ctx->pf_gftt_counts), "select");
+    ctx->det = det_keep;
+    ctx->ls = ctx->stream;
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaEventRecord(ctx->pf_done, ax));
+    ctx->pf_recorded = true;
+    ctx->pf_valid = true;
+    ctx->pf_n = n;
+    for (int i = 0; i < n; ++i) ctx->pf_slots[i] = slots[i];
+    ctx->pf_params = *p;
+    return RDFE_OK;
+}
+
+int rdfe_set_host_sync(rdfe_ctx *ctx, int on) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    ctx->host_sync = on != 0;
+    return RDFE_OK;
 }
 
 int rdfe_detect_batch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p, double *keypoints_xy, int *counts,
@@ -567,7 +636,14 @@ int rdfe_detect_batch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_
     if (gftt_xy) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_xy, ctx->d_gftt_xy, n * k * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (gftt_resp) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_resp, ctx->d_gftt_resp, n * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (gftt_counts) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_counts, ctx->d_gftt_counts, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    return rdfe_sync(ctx);
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->h_overflow, ctx->det.overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // everything this call launched is ordered on the main stream
+    if (*ctx->h_overflow) {
+        cudaMemsetAsync(ctx->det.overflow, 0, sizeof(unsigned), ctx->stream);
+        set_error("corner-candidate buffer overflow (more than %u local maxima in one image)", ctx->det.cand_cap);
+        return RDFE_ERR_OVERFLOW;
+    }
+    return RDFE_OK;
 }
 
 // ------------------------------------------------------------------ track
@@ -607,8 +683,7 @@ int rdfe_track_batch(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots
     std::vector<double> tmp((size_t)n * stride * 2);
     RDFE_CUDA_OK(cudaMemcpyAsync(tmp.data(), ctx->d_xy_b, xyb, cudaMemcpyDeviceToHost, ctx->stream));
     RDFE_CUDA_OK(cudaMemcpyAsync(status, ctx->d_status, (size_t)n * stride, cudaMemcpyDeviceToHost, ctx->stream));
-    rc = rdfe_sync(ctx);
-    if (rc) return rc;
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // the LK launch and these copies are ordered on the main stream
     for (int b = 0; b < n; ++b)
         for (int i = 0; i < counts[b]; ++i) {
             const size_t k = (size_t)b * stride + i;
@@ -672,6 +747,8 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         bool clash = false;                               // new slots still read by the previous step?
         for (int i = 0; i < n; ++i) clash |= ctx->last_step_slots[new_slots[i]] != 0;
         RDFE_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+        if (ctx->pf_recorded) RDFE_CUDA_OK(cudaStreamWaitEvent(ps, ctx->pf_done, 0));   // a detect prefetch may read these slots
+        ctx->pf_valid = false;
         bool renew = false;                               // ... or the NEW slots of step s-2 (Harris(s-2) read them)?
         for (int i = 0; i < n; ++i) renew |= ctx->slot_new_step[new_slots[i]] == (long long)ctx->step_index - 2;
         RDFE_CUDA_OK(cudaStreamWaitEvent(ps, clash ? ctx->ev_step_done[par ^ 1] : ctx->ev_lk_done[par], 0));
@@ -735,6 +812,8 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         return RDFE_OK;
     }
     cudaStream_t ps = ctx->stream;
+    if (ctx->pf_recorded) RDFE_CUDA_OK(cudaStreamWaitEvent(ps, ctx->pf_done, 0));       // a detect prefetch may read these slots
+    ctx->pf_valid = false;
     auto restore = [&]() { ctx->lut = lut_keep; ctx->d_srcptrs = src_keep; ctx->ls = ctx->stream; };
     // ---- preprocess: CLAHE (level 0 + halo), pyramid, Scharr
     ctx->ls = ps;

@@ -183,6 +183,16 @@ struct rdfe_ctx {
     cudaStream_t sel_stream[2], trk_stream, post_stream;
     cudaEvent_t ev_harris_done[2], ev_lk_done[2], ev_entry;
     long long *slot_new_step;     // [num_slots] step index at which the slot was last a step's NEW slot
+    // rdfe_detect_prefetch: Harris + GFTT selection started early on aux_stream2 (candidate scratch det2)
+    bool pf_valid, pf_recorded;
+    int pf_n;
+    int pf_slots[RDFE_MAX_BATCH];
+    rdfe_detect_params pf_params;
+    cudaEvent_t pf_done;
+    float *pf_gftt_xy, *pf_gftt_resp;
+    int *pf_gftt_counts;
+    bool host_sync;               // host-pointer preprocess waits for completion (default) or returns after the upload
+    unsigned *h_overflow;         // pinned copy of det.overflow for the host-pointer detect
     rdfe::DetectScratch det2;     // candidate buffers of odd steps (cand, cand2, count, max; overflow flag shared)
     // optional undistortion in front of preprocess (rdfe_set_undistort): fixed-point remap tables + output staging
     int in_channels;              // 1 gray (default), 3 BGR, 4 BGRA: cvtColor of Odometry::addFrame (rdvio.hpp:42-49)

@@ -144,6 +144,13 @@ class FrontEnd:
             return out, [gxy[i, :gcn[i]].copy() for i in range(n)], [gre[i, :gcn[i]].copy() for i in range(n)]
         return out
 
+    def detect_prefetch(self, slots: Sequence[int], max_points=150, **params):
+        """Start Harris + GFTT selection of preprocessed slots early (rdfe_detect_prefetch); a following detect() on
+        the same slots with the same GFTT parameters only runs the Poisson append."""
+        p = self.detect_params(max_points=max_points, **params)
+        sl = np.asarray(slots, np.int32)
+        N.check(self._L.rdfe_detect_prefetch(self._h, _vp(sl), len(sl), C.byref(p)), "rdfe_detect_prefetch")
+
     def track(self, curr_slots, next_slots, curr: Sequence[np.ndarray], pred: Optional[Sequence[np.ndarray]] = None,
               **params):
         """OpenCvImage::track_keypoints for n image pairs. Returns (next list, status list)."""
@@ -232,6 +239,8 @@ class GpuImage:
         if self._slot is None:
             self._slot = self.fe.acquire()
         self.fe.preprocess([self._slot], [self.image], clip, (tx, ty))
+        if GpuImage._frozen_max_points is not None:      # like the C++ class: selection runs beside the tracking call
+            self.fe.detect_prefetch([self._slot], GpuImage._frozen_max_points)
 
     def detect_keypoints(self, keypoints, max_points=1000, keypoint_distance=10.0):
         """Appends new corners to `keypoints` (list/array of (x,y)); returns the new array."""
