@@ -109,6 +109,37 @@ def test_detect_identical(orc, fe752, frames0, n_existing, radius, max_points):
         fe752.release(s)
 
 
+def test_detect_prefetch_is_transparent(orc, fe752, frames0):
+    """rdfe_detect_prefetch never changes results: used when slots and GFTT parameters match, ignored otherwise,
+    dropped when the slot is preprocessed again or released."""
+    s = _pre(fe752, frames0[0])
+    try:
+        pre0 = orc.clahe(frames0[0])
+        existing = orc.detect_keypoints(pre0, np.zeros((0, 2)), 40, 20.0)[0] + 3.25
+        ref = orc.detect_keypoints(pre0, existing, 150, 20.0)[0]
+        assert np.array_equal(fe752.detect([s], [existing], 150, 20.0)[0], ref)
+        fe752.detect_prefetch([s], 150)
+        assert np.array_equal(fe752.detect([s], [existing], 150, 20.0)[0], ref)           # consumed
+        fe752.detect_prefetch([s], 150)
+        assert np.array_equal(fe752.detect([s], [existing], 150, 12.0)[0],               # Poisson radius may differ
+                              orc.detect_keypoints(pre0, existing, 150, 12.0)[0])
+        fe752.detect_prefetch([s], 100)                                                   # other max_points: ignored
+        assert np.array_equal(fe752.detect([s], [existing], 150, 20.0)[0], ref)
+        fe752.detect_prefetch([s], 150)                                                   # stale after a new preprocess
+        fe752.preprocess([s], [frames0[1]])
+        ref1 = orc.detect_keypoints(orc.clahe(frames0[1]), np.zeros((0, 2)), 150, 20.0)[0]
+        assert np.array_equal(fe752.detect([s], [np.zeros((0, 2))], 150, 20.0)[0], ref1)
+        fe752.detect_prefetch([s], 150)                                                   # stale after release + reuse
+    finally:
+        fe752.release(s)
+    s2 = _pre(fe752, frames0[2])
+    try:
+        ref2 = orc.detect_keypoints(orc.clahe(frames0[2]), np.zeros((0, 2)), 150, 20.0)[0]
+        assert np.array_equal(fe752.detect([s2], [np.zeros((0, 2))], 150, 20.0)[0], ref2)
+    finally:
+        fe752.release(s2)
+
+
 def _track_case(orc, fe, f0, f1, pts, pred, win=21, max_level=3):
     s0, s1 = _pre(fe, f0), _pre(fe, f1)
     try:
