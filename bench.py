@@ -413,6 +413,12 @@ def main_b200(args, wl):
                     "algorithmic_bytes_per_launch": per_launch_bytes, "us_per_launch": prof[dom]["us_per_launch"],
                     "share_of_step": prof[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in prof.values()), 1e-12)}
     step_frac = (value / world) * total_bytes / 1e9 / hbm_peak
+    if prof:   # every kernel against the same HBM peak (algorithmic bytes of its stage / its serialised time)
+        for kname, v in prof.items():
+            sb = stage_bytes.get(kname, 0) * S
+            v["algorithmic_bytes_per_step"] = sb
+            v["achieved_gbs"] = (sb / (v["ms_per_step"] * 1e-3) / 1e9) if v["ms_per_step"] > 0 else 0.0
+            v["hbm_frac"] = v["achieved_gbs"] / hbm_peak
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
