@@ -239,19 +239,22 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
     __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
     __shared__ unsigned s_cnt[HW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * HW_WARPS + warp;
-    if (item >= n_items) return;
-    const int b = blockIdx.y, slot = slots.v[b];
     const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
-    const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * hr_rows;
-    const uint8_t *org = pyr.image_origin(0, slot);
-    if (lane == 0) s_cnt[warp] = 0u;
-    __syncwarp();
-    // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+HR_ROWS+2 all inside the image, and the
-    // outputs stay off the 1-px frame
-    const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
-    if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
-    else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+    // work item = (image, strip), flattened so that consecutive warps take consecutive strips of one image; written
+    // as a grid-stride loop (a persistent grid of 2-3 CTAs per SM was measured: slower than one warp per item)
+    const int total = n_items * slots.n;
+    for (int wi = blockIdx.x * HW_WARPS + warp; wi < total; wi += gridDim.x * HW_WARPS) {
+        const int b = wi / n_items, item = wi - b * n_items, slot = slots.v[b];
+        const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * hr_rows;
+        const uint8_t *org = pyr.image_origin(0, slot);
+        if (lane == 0) s_cnt[warp] = 0u;
+        __syncwarp();
+        // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+hr_rows+2 all inside the image, and the
+        // outputs stay off the 1-px frame
+        const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
+        if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+        else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+    }
 }
 
 __global__ void detect_reset_kernel(DetectScratch det, int n) {
@@ -266,7 +269,8 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
     const int hr_rows = adaptive_strip_rows(g.h, tiles_x * slots.n, 8, HR_ROWS);
     const int strips = (g.h + hr_rows - 1) / hr_rows;
     const int n_items = tiles_x * strips;
-    dim3 grid((n_items + HW_WARPS - 1) / HW_WARPS, slots.n);
+    const int total = n_items * slots.n;
+    dim3 grid((total + HW_WARPS - 1) / HW_WARPS);     // one warp per (image, strip); the kernel's loop also accepts fewer
     if (p.harris_fma)
         RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items, hr_rows)));
     else
