@@ -225,11 +225,11 @@ clahe_apply_kernel(const uint8_t *const *__restrict__ src, size_t pitch, int src
 __global__ void __launch_bounds__(256)
 clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, ClaheParams cp, ApplyBands bands,
                         const uint8_t *__restrict__ lut, Pyramid pyr, SlotList slots) {
-    // shared memory: [ncx][256] float4 = the four tile-LUT values of a pixel (l11, l12, l21, l22) already as
-    // floats (one 16-byte gather per pixel, no conversions in the pixel loop), then xa, 1-xa and the cell
-    // table offset per column.
-    extern __shared__ float4 smem_f4[];
-    float4 *comb = smem_f4;
+    // shared memory: [ncx][256] entries of the four tile-LUT values of a pixel (l11, l12, l21, l22) as bf16 (exact
+    // for 0..255; float = bits << 16), 8 bytes per entry: one 8-byte gather per pixel -- the kernel is bound by
+    // shared-memory wavefronts, a float4 entry costs twice as many -- then xa, 1-xa and the cell table offset per column.
+    extern __shared__ uint2 smem_u2[];
+    uint2 *comb = smem_u2;
     const int ncx = cp.tiles_x + 1;
     const int W = cp.W, H = cp.H, win = pyr.win;
     float *xa_s = reinterpret_cast<float *>(comb + ncx * 256);          // [W]
@@ -244,7 +244,8 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
     for (int i = tid; i < ncx * 256; i += 256) {
         const int c = i >> 8, v = i & 255;
         const int o1 = max(c - 1, 0) * 256 + v, o2 = min(c, cp.tiles_x - 1) * 256 + v;
-        comb[i] = make_float4(u8_to_float(L1[o1]), u8_to_float(L1[o2]), u8_to_float(L2[o1]), u8_to_float(L2[o2]));
+        auto bf = [](unsigned v) { return __float_as_uint(u8_to_float(v)) >> 16; };     // exact: 8 significant bits
+        comb[i] = make_uint2(bf(L1[o1]) | (bf(L1[o2]) << 16), bf(L2[o1]) | (bf(L2[o2]) << 16));
     }
     for (int x = tid; x < W; x += 256) {
         const float txf = (float)x * cp.inv_tw - 0.5f;
@@ -253,7 +254,7 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
         xa1_s[x] = 1.0f - xa;
         int c = 0;
         while (c < ncx - 1 && x >= cp.xb[c + 1]) ++c;
-        cb_s[x] = (uint32_t)c << 12;                                    // cell * 256 entries * 16 bytes
+        cb_s[x] = (uint32_t)c << 11;                                    // cell * 256 entries * 8 bytes
     }
     __syncthreads();
 
@@ -281,8 +282,10 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float xa = xas[i], xa1 = xbs[i];
-                const float4 e = *reinterpret_cast<const float4 *>(combb + cbs[i] + 16u * __byte_perm(px, 0u, 0x4440u | (unsigned)i));
-                const float res = (e.x * xa1 + e.y * xa) * ya1 + (e.z * xa1 + e.w * xa) * ya;
+                const uint2 e = *reinterpret_cast<const uint2 *>(combb + cbs[i] + 8u * __byte_perm(px, 0u, 0x4440u | (unsigned)i));
+                const float l11 = __uint_as_float(e.x << 16), l12 = __uint_as_float(e.x & 0xFFFF0000u);
+                const float l21 = __uint_as_float(e.y << 16), l22 = __uint_as_float(e.y & 0xFFFF0000u);
+                const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
                 rb[i] = __float_as_uint(res + 12582912.0f);
             }
             return __byte_perm(__byte_perm(rb[0], rb[1], 0x0040u), __byte_perm(rb[2], rb[3], 0x0040u), 0x5410u);
@@ -366,7 +369,7 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
         }
     dim3 g2(bands.nbands, slots.n);
     const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t) + (size_t)((cp.W + 3) & ~3) * 8;
-    const size_t smem_fast = (size_t)(cp.tiles_x + 1) * 256 * sizeof(float4) + (size_t)cp.W * 12;
+    const size_t smem_fast = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint2) + (size_t)cp.W * 12;
     if (src_vec4 && cp.W % 4 == 0 && smem_fast <= 100 * 1024) {
         static size_t s_attr = 0;
         if (smem_fast > 48 * 1024 && smem_fast > s_attr) {
