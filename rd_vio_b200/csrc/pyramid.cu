@@ -28,9 +28,10 @@ constexpr int PD_ROWS = 8;             // output rows per warp strip at full bat
 __global__ void __launch_bounds__(PW_WARPS * 32)
 pyrdown_kernel(Pyramid pyr, SlotList slots, int l, int tiles_x, int n_items, int pd_rows) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * PW_WARPS + warp;
-    if (item >= n_items) return;
-    const int slot = slots.v[blockIdx.y];
+    const int wi = blockIdx.x * PW_WARPS + warp;            // flattened (image, strip): no idle warps per image
+    if (wi >= n_items * slots.n) return;
+    const int bimg = wi / n_items, item = wi - bimg * n_items;
+    const int slot = slots.v[bimg];
     const LevelGeom gs = pyr.lv[l], gd = pyr.lv[l + 1];
     const uint8_t *src = pyr.image_origin(l, slot);
     uint8_t *dst = pyr.image_origin(l + 1, slot);
@@ -104,15 +105,21 @@ struct ItemTable {
     int first[RDFE_MAX_LEVELS + 1];   // work items (warps) of each level
     int tiles_x[RDFE_MAX_LEVELS];
     int rows[RDFE_MAX_LEVELS];        // strip height of each level
+    int base[RDFE_MAX_LEVELS + 1];    // first flattened (level, image, strip) index of each level
 };
 
 __global__ void __launch_bounds__(PW_WARPS * 32)
 scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = blockIdx.z;                                // level
-    const int item = blockIdx.x * PW_WARPS + warp;
-    if (item >= tt.first[l]) return;                         // tt.first[l] = work items of this level
-    const int slot = slots.v[blockIdx.y];
+    // flattened (level, image, strip) work items: tt.first[l] = items of level l per image, tt.base[l] = first
+    // flattened index of level l
+    int wi = blockIdx.x * PW_WARPS + warp;
+    if (wi >= tt.base[pyr.nlevels]) return;
+    int l = 0;
+    while (wi >= tt.base[l + 1]) ++l;
+    wi -= tt.base[l];
+    const int bimg = wi / tt.first[l], item = wi - bimg * tt.first[l];
+    const int slot = slots.v[bimg];
     // level geometry into registers once (the loop below only bumps pointers)
     const int gw = pyr.lv[l].w, gh = pyr.lv[l].h, ipitch = pyr.lv[l].ipitch, dpitch = pyr.lv[l].dpitch;
     const int tiles_x = tt.tiles_x[l];
@@ -187,20 +194,20 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
         const int pd_rows = adaptive_strip_rows(gd.h, tiles_x * slots.n, 2, PD_ROWS);
         const int strips = (gd.h + pd_rows - 1) / pd_rows;
         const int n_items = tiles_x * strips;
-        dim3 grid((n_items + PW_WARPS - 1) / PW_WARPS, slots.n);
+        dim3 grid((n_items * slots.n + PW_WARPS - 1) / PW_WARPS);
         RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, l, tiles_x, n_items, pd_rows)));
         ++launches;
     }
     ItemTable tt;
-    int max_items = 0;
+    tt.base[0] = 0;
     for (int l = 0; l < pyr.nlevels; ++l) {
         const LevelGeom &g = pyr.lv[l];
         tt.tiles_x[l] = (g.w + 127) / 128;
         tt.rows[l] = adaptive_strip_rows(g.h, tt.tiles_x[l] * slots.n, 4, SC_ROWS);
-        tt.first[l] = tt.tiles_x[l] * ((g.h + tt.rows[l] - 1) / tt.rows[l]);      // work items (warps) of level l
-        max_items = tt.first[l] > max_items ? tt.first[l] : max_items;
+        tt.first[l] = tt.tiles_x[l] * ((g.h + tt.rows[l] - 1) / tt.rows[l]);      // work items (warps) of level l per image
+        tt.base[l + 1] = tt.base[l] + tt.first[l] * slots.n;
     }
-    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<dim3((max_items + PW_WARPS - 1) / PW_WARPS, slots.n, pyr.nlevels), PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, tt)));
+    RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<(tt.base[pyr.nlevels] + PW_WARPS - 1) / PW_WARPS, PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, tt)));
     return launches + 1;
 }
 
