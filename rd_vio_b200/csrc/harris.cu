@@ -89,11 +89,16 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
     for (int i = 0; i < 6; ++i) { Rm[i] = -INFINITY; Rc[i] = -INFINITY; }
     float tmax = 0.0f;
 
+    // Candidate keys are staged in the warp's shared-memory buffer.  Slots come from one shared-memory atomic per
+    // lane that has candidates; the fill count is mirrored in a warp-uniform register (REDUX of the per-lane counts),
+    // so the flush decision needs neither a shared-memory read nor a warp barrier.
+    unsigned nstaged = 0;
     auto flush = [&]() {
-        const unsigned nb = *cnt;
+        const unsigned nb = nstaged;
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(&det.cand_count[b], nb);
         base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();                                    // the staged keys of all lanes are visible
         for (unsigned i = lane; i < nb; i += 32) {
             const unsigned pos = base + i;
             if (pos < det.cand_cap) det.cand[(size_t)b * det.cand_cap + pos] = buf[i];
@@ -101,6 +106,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
         }
         __syncwarp();
         if (lane == 0) *cnt = 0u;
+        nstaged = 0;
         __syncwarp();
     };
 
@@ -204,17 +210,16 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
                 if (ve > 0.0f && ve >= m) cmask |= 1u << i;
                 if (out_lane) tmax = fmaxf(tmax, v);         // -inf outside the image never wins
             }
-            if (cmask && nrow_ok) {
-                // stage the keys: shared-memory atomic slot allocation, flushed by the warp when filling up
+            if (!nrow_ok) cmask = 0;
+            const unsigned nmine = __popc(cmask);
+            if (nmine) {
+                unsigned pos = atomicAdd(cnt, nmine);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (cmask & (1u << i)) {
-                        const unsigned pos = atomicAdd(cnt, 1u);
-                        buf[pos] = ((unsigned long long)__float_as_uint(Rc[i + 1]) << 32) | (addr_row + (unsigned)i);
-                    }
+                    if (cmask & (1u << i)) buf[pos++] = ((unsigned long long)__float_as_uint(Rc[i + 1]) << 32) | (addr_row + (unsigned)i);
             }
-            __syncwarp();
-            if (*cnt > (unsigned)(HW_BUF - 128)) flush();    // warp-uniform: a step adds at most 120 keys
+            nstaged += __reduce_add_sync(0xffffffffu, nmine);
+            if (nstaged > (unsigned)(HW_BUF - 128)) flush();    // warp-uniform: a step adds at most 120 keys
         }
         addr_row += (unsigned)W;
         // roll the response rows: Rm <- hmax3(Rc), Rc <- Rn
@@ -226,8 +231,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
 #pragma unroll
         for (int i = 0; i < 4; ++i) { dA[i] = dB[i]; dB[i] = dN[i]; sA[i] = sB[i]; sB[i] = sN[i]; }
     }
-    __syncwarp();
-    if (*cnt) flush();
+    if (nstaged) flush();
     const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
     if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
 }
