@@ -1,7 +1,7 @@
 """Dynamic (executed) instruction mix of a kernel from an .ncu-rep source page."""
 import csv, subprocess, sys, collections
 rep, kernel = sys.argv[1], sys.argv[2]
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kernel], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]; ci = {h: i for i, h in enumerate(hdr)}
 agg = collections.Counter(); tot = 0

@@ -2,7 +2,7 @@
 import csv, subprocess, sys
 rep, kernel = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kernel], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}

@@ -2,7 +2,7 @@
 import csv, subprocess, sys
 rep, kernel = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda", "--csv", "--kernel-name", kernel],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda", "--csv", "--kernel-name", "regex:" + kernel],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "# Samples" in r)

@@ -1,7 +1,7 @@
 """Stall samples between consecutive barriers/branches of a kernel (SASS view) -- coarse phase attribution."""
 import csv, subprocess, sys
 rep, kernel = sys.argv[1], sys.argv[2]
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kernel], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]; ci = {h: i for i, h in enumerate(hdr)}
 seg, segs, tot, n = 0, [], 0, 0
