@@ -33,7 +33,7 @@ template <> struct LKCfg<21> {
     static constexpr bool PACKED = false;
 };
 template <> struct LKCfg<31> {
-    static constexpr int SEG = 8, NSEG = 4, JW = 64, JH = 48, DW = 36, DH = 32, MARGIN = 8, WARPS = 4, MIN_CTAS = 2;
+    static constexpr int SEG = 8, NSEG = 4, JW = 64, JH = 48, DW = 36, DH = 32, MARGIN = 8, WARPS = 4, MIN_CTAS = 3;
     static constexpr bool PACKED = true;
 };
 
