@@ -183,11 +183,16 @@ RDFE_API int rdfe_set_undistort(rdfe_ctx *ctx, const float *K, const float *D);
  * (bit-identical to cv::cvtColor), after the optional undistortion (which then runs per channel). */
 RDFE_API int rdfe_set_input_format(rdfe_ctx *ctx, int channels);
 
-/* Cross-step pipelining for rdfe_frontend_step_dev (off by default).  When on, the preprocess stage of a call
- * runs on an internal stream and only waits for the step BEFORE the previous one, so it overlaps the previous
- * step's tracking/detection -- provided its new slots were not touched by the previous step (use three slot
- * sets in rotation; otherwise the call silently serialises).  Requirement: the source images must already be
- * complete in device memory when the call is made (they are not ordered against the context stream). */
+/* Cross-step pipelining for rdfe_frontend_step_dev (off by default).  When on, every kernel class of a step runs on
+ * its own internal stream (preprocess, Harris, selection, LK, Poisson append) and events carry only the data
+ * dependences, so the preprocess stage of step s overlaps step s-1: it waits for LK of step s-2, the last reader of
+ * the slot set it rewrites -- provided its new slots were not touched by the previous step (use three slot sets in
+ * rotation; otherwise the call silently serialises).  LK waits for the work already enqueued on the context's stream
+ * (the caller's keypoint buffers) and the context's stream waits for the end of the step, so results are ordered for
+ * the caller as usual.  Requirement: the source images must already be complete in device memory when the call is
+ * made (they are not ordered against the context stream).  The preprocess stream runs at a higher priority than the
+ * others (environment variable RDFE_PRIO="pre,harris,select,lk,poisson" overrides the five levels); a caller stream
+ * created with a high priority keeps its own small copies from queueing behind the large grids. */
 RDFE_API int rdfe_set_pipelining(rdfe_ctx *ctx, int on);
 
 /* Host-buffer form of the same step, pipelined two deep: submit() uploads the frames and keypoints on a copy
