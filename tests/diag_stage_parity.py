@@ -1,4 +1,4 @@
-"""First-contact GPU diagnostic: per-stage parity statistics against the oracle + rough timings."""
+"""Diagnostic (run by hand on a GPU box, not collected by pytest): per-stage parity statistics against the oracle + rough timings."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
