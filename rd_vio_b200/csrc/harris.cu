@@ -31,7 +31,9 @@ namespace rdfe {
 //   * the 3-tap row smoothing ((k0*p[x-1]) + k1*p[x]) + k0*p[x+1] is not associative, so on the
 //     mirrored columns x = -1 and x = W it is evaluated in mirrored order.
 // All float64 sums are exact (9 terms, exponent spread < 2^29), hence order independent.
-constexpr int HR_ROWS = 44;            // output rows per warp strip at full batches (adaptive_strip_rows)
+constexpr int HR_ROWS = 80;            // output rows per warp strip at full batches (adaptive_strip_rows).  Taller strips
+                                       // = fewer halo rows: in the pipelined step 44 -> 80 rows gives +1.5 % (120 rows +3 %, but
+                                       // then the kernel alone suffers from a 1.01-wave grid)
 constexpr int HR_COLS = 120;           // output columns per warp (lanes 1..30)
 constexpr int HW_WARPS = 4;            // warps per CTA
 constexpr int HW_BUF = 256;            // per-warp candidate staging (keys)
