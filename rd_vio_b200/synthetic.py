@@ -76,6 +76,17 @@ class SyntheticStream:
         r = self._amp_r * np.sin(w + self._phase[3:])
         return _rot(*r), t            # camera-to-world rotation, camera centre
 
+    def K(self):
+        """3x3 intrinsic matrix of the stream (Frame::K)."""
+        return np.array([[self.fx, 0.0, self.cx], [0.0, self.fy, self.cy], [0.0, 0.0, 1.0]])
+
+    def gyro_delta(self, k):
+        """Rotation increment from frame k to k+1 as IMU pre-integration reports it (delta.q as a matrix, R_k^T R_k+1;
+        camera and IMU frames coincide in the synthetic rig)."""
+        R0, _ = self.pose(k)
+        R1, _ = self.pose(k + 1)
+        return R0.T @ R1
+
     def _hit(self, R, c, rays):
         """Intersect rays with the planes; returns world XY, plane index per ray."""
         d = rays @ R.T

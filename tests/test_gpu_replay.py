@@ -128,3 +128,27 @@ def test_cpp_plugin_replay_200_frames(tmp_path):
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, "plugin_latency.txt"), "w") as f:
             f.write(lat[0] + "\n")
+
+
+def test_feature_tracker_replay_with_imu_prediction():
+    """the plugin driven by the reference's callers (rd_vio_b200/frame.py: pixels from unit
+    bearings through K, predictions = bearings rotated by the gyro increment, track-length-ordered Poisson filter,
+    detect on what survived), 40 frames, GPU plugin against the same loop on the CPU oracle: identical track ids
+    and keypoint counts in every frame, positions within 0.01 px."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from frame_helpers import OracleImage, replay
+    from rd_vio_b200.frontend import FrontEnd, GpuImage
+    from rd_vio_b200.synthetic import SyntheticStream
+    st = SyntheticStream(5, 752, 480, period=64)
+    ref = replay(st, 40, lambda im, t: OracleImage(im, t))
+    GpuImage.reset_frozen_parameters()
+    with FrontEnd(752, 480, 3, 21, num_slots=4, max_points=1024) as fe:
+        got = replay(st, 40, lambda im, t: GpuImage(fe, im, t))
+    GpuImage.reset_frozen_parameters()
+    long_tracks = 0
+    for i, ((kp, ids), (rkp, rids)) in enumerate(zip(got, ref)):
+        assert ids == rids, f"frame {i}: track ids differ"
+        assert kp.shape == rkp.shape and np.abs(kp - rkp).max() <= 0.01, f"frame {i}"
+        long_tracks = max(long_tracks, sum(1 for t in ids if t >= 0))
+    assert long_tracks >= 80          # the prediction path really carried tracks from frame to frame
