@@ -15,6 +15,7 @@
 // thr = max(R)*q needs the frame maximum, so this kernel emits every POSITIVE 3x3 local
 // maximum as a 64-bit key (float bits << 32 | y*W+x) plus the per-frame maximum; the
 // select kernel applies thr.  The response map itself never goes to HBM on the hot path.
+#include <cstdlib>
 #include "fe_internal.cuh"
 
 namespace rdfe {
@@ -61,14 +62,27 @@ __device__ __forceinline__ double shfl_down_d(double v) {
 
 // One strip (HR_ROWS x 120 outputs) by one warp.  BORDER = false is the lean variant for strips whose
 // whole 128-column x (rows+6)-row footprint lies inside the image: no mirror/sign/validity logic at all.
+//
+// Narrow last column tile (BORDER only): when the columns left over after the full 120-column tiles fit in 8 (14)
+// output lanes, the warp is split into 3 (2) groups of GL = 10 (16) lanes -- first and last lane of a group are its
+// apron -- and group g walks strip number first_strip + g of that tile, so the lanes a single strip would leave
+// idle work on the strips below it (752 = 6 x 120 + 32: 38 instead of 42 warp strips per image).  The shuffles
+// stay warp-wide: what crosses a group boundary only reaches apron columns whose results are never used, exactly
+// like lanes 0 and 31 of the one-group case.  y0, the row count and every row predicate are then per lane; the loop
+// trip count, the staging flush and the REDUX stay warp-uniform (group 0 always has the most rows).
 template <bool kFma, bool BORDER>
-__device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0, int hr_rows, float k,
-                                             const DetectScratch &det, int b, float *__restrict__ response,
+__device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0w, int hr_rows, int gl_lanes,
+                                             int n_groups, float k, const DetectScratch &det, int b, float *__restrict__ response,
                                              unsigned long long *buf, unsigned *cnt) {
     const int lane = threadIdx.x & 31;
-    const int c0 = x0 - 4 + 4 * lane;                       // first of this lane's 4 columns
-    const bool ld_ok = BORDER ? ((c0 + 3 <= W + 20) && (c0 >= -20)) : true;   // inside the materialised halo
-    const bool out_lane = lane >= 1 && lane <= 30;          // lanes 0 and 31 are apron
+    const int GL = BORDER ? gl_lanes : 32;
+    const int grp = BORDER ? lane / GL : 0;
+    const int gl = lane - grp * GL;                         // lane within its group
+    const int y0 = y0w + grp * hr_rows;                     // first output row of this lane's strip
+    const bool active = !BORDER || (grp < n_groups && y0 < H);
+    const int c0 = x0 - 4 + 4 * gl;                         // first of this lane's 4 columns
+    const bool ld_ok = BORDER ? (active && (c0 + 3 <= W + 20) && (c0 >= -20)) : true;   // inside the materialised halo
+    const bool out_lane = active && gl >= 1 && gl <= GL - 2;   // first and last lane of a group are apron
     const double sc = 1.0 / (4.0 * 3.0 * 255.0);
     const float k0 = (float)sc, k1 = (float)(2.0 * sc);
     // per-column flags (BORDER only)
@@ -112,8 +126,9 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
         __syncwarp();
     };
 
-    const int rows = min(hr_rows, H - y0);
-    const int steps = rows + 6;
+    const int rows = active ? min(hr_rows, H - y0) : 0;    // of this lane's strip
+    const int steps = min(hr_rows, H - y0w) + 6;            // warp-uniform trip count
+    const int my_steps = BORDER ? rows + 6 : steps;         // rows this lane may read (its strip ends earlier at the bottom)
     // software pipelining: the pixel words of rows j+1, j+2 are in flight while row j is processed
     const uint8_t *rowp = org + (ptrdiff_t)(y0 - 3) * ipitch + c0;
     unsigned wq0 = 0, wq1 = 0;
@@ -126,7 +141,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
         // ---- pixels c0-1 .. c0+4 of row y = y0-3+j as floats
         const unsigned w = wq0;
         wq0 = wq1;
-        if (ld_ok && j + 2 < steps) wq1 = *reinterpret_cast<const unsigned *>(rowp);
+        if (ld_ok && j + 2 < my_steps) wq1 = *reinterpret_cast<const unsigned *>(rowp);
         rowp += ipitch;
         const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
         float p[6];
@@ -200,8 +215,8 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
         }
         // ---- NMS for row n = q-1: rows Rm (n-1, reduced to hmax3), Rc (n), Rn (n+1)
         const int n = q - 1;
-        const bool nrow_ok = (n >= y0) && (n < y0 + rows) && (!BORDER || ((n >= 1) && (n < H - 1)));
-        if (n >= y0 && n < y0 + rows) {
+        const bool nrow_ok = (n < y0 + rows) && (!BORDER || ((n >= 1) && (n < H - 1)));
+        if (j >= 6) {                                        // n >= y0 (n < y0 + rows holds for the tallest group)
             unsigned cmask = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -241,7 +256,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
 template <bool kFma>
 __global__ void __launch_bounds__(HW_WARPS * 32)
 harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
-                  int n_items, int hr_rows) {
+                  int strips, int gl_narrow, int n_items, int hr_rows) {
     __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
     __shared__ unsigned s_cnt[HW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -251,16 +266,33 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
     const int total = n_items * slots.n;
     for (int wi = blockIdx.x * HW_WARPS + warp; wi < total; wi += gridDim.x * HW_WARPS) {
         const int b = wi / n_items, item = wi - b * n_items, slot = slots.v[b];
-        const int x0 = (item % tiles_x) * HR_COLS, y0 = (item / tiles_x) * hr_rows;
+        // items of an image: tiles_x full-width tiles x strips, then the narrow last tile, n_groups strips per item
+        int x0, y0, gl_lanes = 32, n_groups = 1;
+        if (item < tiles_x * strips) { x0 = (item % tiles_x) * HR_COLS; y0 = (item / tiles_x) * hr_rows; }
+        else {
+            gl_lanes = gl_narrow; n_groups = gl_narrow == 10 ? 3 : 2;
+            x0 = tiles_x * HR_COLS; y0 = (item - tiles_x * strips) * n_groups * hr_rows;
+        }
         const uint8_t *org = pyr.image_origin(0, slot);
         if (lane == 0) s_cnt[warp] = 0u;
         __syncwarp();
         // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+hr_rows+2 all inside the image, and the
         // outputs stay off the 1-px frame
         const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
-        if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
-        else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+        if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+        else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, k, det, b, response, s_buf[warp], &s_cnt[warp]);
     }
+}
+
+// Experiment switches (environment, read once): RDFE_HARRIS_ROWS = strip height at full batches, RDFE_HARRIS_NARROW=0
+// walks the narrow last tile one strip per warp like the full tiles.
+static int harris_max_rows() {
+    static const int v = [] { const char *e = getenv("RDFE_HARRIS_ROWS"); const int r = e ? atoi(e) : 0; return r >= 8 && r <= 1080 ? (r + 3) & ~3 : HR_ROWS; }();
+    return v;
+}
+static bool harris_narrow_enabled() {
+    static const bool v = [] { const char *e = getenv("RDFE_HARRIS_NARROW"); return !(e && e[0] == '0'); }();
+    return v;
 }
 
 __global__ void detect_reset_kernel(DetectScratch det, int n) {
@@ -271,16 +303,21 @@ __global__ void detect_reset_kernel(DetectScratch det, int n) {
 int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_response) {
     const LevelGeom &g = ctx->pyr.lv[0];
     detect_reset_kernel<<<1, RDFE_MAX_BATCH, 0, ctx->ls>>>(ctx->det, slots.n);
-    const int tiles_x = (g.w + HR_COLS - 1) / HR_COLS;
-    const int hr_rows = adaptive_strip_rows(g.h, tiles_x * slots.n, 8, HR_ROWS);
+    const int tiles_all = (g.w + HR_COLS - 1) / HR_COLS;
+    const int hr_rows = adaptive_strip_rows(g.h, tiles_all * slots.n, 8, harris_max_rows());
     const int strips = (g.h + hr_rows - 1) / hr_rows;
-    const int n_items = tiles_x * strips;
+    // narrow last tile: <= 32 (56) leftover columns are walked by 3 (2) lane groups, one strip each (harris_strip)
+    const int left = g.w - (tiles_all - 1) * HR_COLS;
+    const int gl_narrow = harris_narrow_enabled() ? (left <= 32 ? 10 : left <= 56 ? 16 : 0) : 0;
+    const int n_groups = gl_narrow == 10 ? 3 : 2;
+    const int tiles_x = gl_narrow ? tiles_all - 1 : tiles_all;          // full-width tiles
+    const int n_items = tiles_x * strips + (gl_narrow ? (strips + n_groups - 1) / n_groups : 0);
     const int total = n_items * slots.n;
     dim3 grid((total + HW_WARPS - 1) / HW_WARPS);     // one warp per (image, strip); the kernel's loop also accepts fewer
     if (p.harris_fma)
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items, hr_rows)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
     else
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, n_items, hr_rows)));
+        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
     return 2;
 }
 

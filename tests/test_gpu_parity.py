@@ -443,3 +443,37 @@ def test_color_ingest_bit_exact(orc, channels, undistort):
         fe.preprocess([s0], [img])
         assert np.array_equal(fe.download_level(s0, 0, 3), gray), "ingest (gray) frame differs"
         assert np.array_equal(fe.download_level(s0, 0, 0), orc.clahe(gray))
+
+
+@pytest.mark.parametrize("shape", [(478, 750), (300, 400), (100, 152), (241, 277), (130, 296), (97, 121), (64, 56)])
+def test_harris_narrow_last_tile(orc, shape):
+    """Widths whose last 120-column tile holds <= 32 / <= 56 columns: that tile is walked by 3 / 2 lane groups, one
+    strip each (harris.cu), including bottom strips shorter than the others and groups without a strip.  Response map
+    bit-exact in both float orders, corners identical."""
+    from rd_vio_b200.frontend import FrontEnd
+    H, W = shape
+    img = random_image(H, W, seed=W * 7 + H)
+    pre = orc.clahe(img)
+    with FrontEnd(W, H, max_level=1 if min(H, W) > 90 else 0, win=21, num_slots=1, max_points=256) as fe:
+        s = _pre(fe, img)
+        for fma in (0, 1):
+            got, ref = fe.harris_response(s, harris_fma=fma), orc.harris(pre, 0.04, mode=fma)
+            assert np.array_equal(got, ref), f"fma={fma}: Harris map differs in {(got != ref).sum()} px"
+        ref_kp, gxy_ref, gre_ref = orc.detect_keypoints(pre, np.zeros((0, 2)), 150, 20.0)
+        kp, gxy, gre = fe.detect([s], [np.zeros((0, 2))], 150, 20.0, return_gftt=True)
+        assert np.array_equal(gxy[0], gxy_ref) and np.array_equal(gre[0], gre_ref) and np.array_equal(kp[0], ref_kp)
+
+
+def test_detect_full_height_strips_batch(orc):
+    """48 frames of 752x480 in one call: the Harris strips have their full-batch height (adaptive_strip_rows) and the
+    32-column last tile is walked three strips per warp; every frame's corners against the oracle."""
+    from rd_vio_b200.frontend import FrontEnd
+    n = 48
+    imgs = [random_image(480, 752, 900 + i) for i in range(n)]
+    with FrontEnd(752, 480, max_level=3, win=21, num_slots=n, max_points=256) as fe:
+        slots = [fe.acquire() for _ in range(n)]
+        fe.preprocess(slots, imgs)
+        kps = fe.detect(slots, [np.zeros((0, 2))] * n, 150, 20.0)
+        for i in range(n):
+            ref = orc.detect_keypoints(orc.clahe(imgs[i]), np.zeros((0, 2)), 150, 20.0)[0]
+            assert np.array_equal(kps[i], ref), f"frame {i}"
