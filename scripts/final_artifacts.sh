@@ -8,3 +8,6 @@ python bench.py --workload hd --streams 32 --no-cpu-baseline > gpurun_out/bench_
 C='python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --profile-steps 0'
 $C > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -c 400 --csv --log-file gpurun_out/launches_final.csv $C > gpurun_out/ncu_launches.log 2>&1
 echo "ncu rc $?"; wc -l gpurun_out/launches_final.csv
+# one --set full capture of the kernel changed last (harris_nms after the narrow-tile change), steady state
+timeout 120 ncu --set full --clock-control none --import-source on -k regex:harris_nms -s 12 -c 1 -f -o gpurun_out/prof_r1_harris_narrow $C > gpurun_out/ncu_full_harris.log 2>&1
+echo "ncu full rc $?"
