@@ -393,7 +393,7 @@ def main_b200(args, wl):
 
     # ---- roofline of the dominant kernel
     hbm_peak, peak_src = peaks()
-    total_bytes, stage_bytes = WL.algorithmic_bytes(W, H, NP, wl["max_level"], wl["win"])
+    total_bytes, stage_bytes = WL.algorithmic_bytes(W, H, NP, wl["max_level"], wl["win"], undistort=bool(args.undistort))
     roofline = None
     if prof:
         dom = max(prof, key=lambda kname: prof[kname]["ms_per_step"])

@@ -22,8 +22,10 @@ WORKLOADS = {
 }
 
 
-def algorithmic_bytes(width, height, points, max_level, win):
-    """SURVEY.md 8(d) stage-materialised byte model per frame. Returns (total, per-stage dict)."""
+def algorithmic_bytes(width, height, points, max_level, win, undistort=False):
+    """SURVEY.md 8(d) stage-materialised byte model per frame. Returns (total, per-stage dict).
+    undistort=True adds the ingest stage of 8(f) rank 1 (raw frame read + undistorted frame written = 2S; the 6 B/px
+    fixed-point map is one per context and shared by every frame of a launch, so it is not charged per frame)."""
     sizes = []
     w, h = width, height
     for l in range(max_level + 1):
@@ -44,6 +46,8 @@ def algorithmic_bytes(width, height, points, max_level, win):
         "select": 0,
         "poisson_append": 0,
     }
+    if undistort:
+        stages["undistort"] = 2 * S
     return sum(stages.values()), stages
 
 
