@@ -159,7 +159,7 @@ static int stage_sources(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *
         ptrs[RDFE_MAX_BATCH + i] = ctx->und_plane + (size_t)slots[i] * ctx->gray_slot;
     }
     RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_srcptrs, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, st));
-    int rc = check_launch(ctx, launch_undistort(ctx, n, ctx->d_srcptrs, pitch, (uint8_t *const *)(ctx->d_srcptrs + RDFE_MAX_BATCH), ctx->gray_pitch), "ingest");
+    int rc = check_launch(ctx, launch_undistort(ctx, n, ctx->d_srcptrs, pitch, vec4, (uint8_t *const *)(ctx->d_srcptrs + RDFE_MAX_BATCH), ctx->gray_pitch), "ingest");
     if (rc) return rc;
     *d_src_out = ctx->d_srcptrs + RDFE_MAX_BATCH; *pitch_out = ctx->gray_pitch; *vec4_out = 1;
     return RDFE_OK;

@@ -291,7 +291,7 @@ int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_det
                        float *d_gftt_resp, int *d_gftt_counts);
 int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, const float *d_gftt_xy,
                           const int *d_gftt_counts, double *d_xy, int *d_counts, int stride);
-int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t src_pitch, uint8_t *const *d_dst,
+int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t src_pitch, int src_vec4, uint8_t *const *d_dst,
                      size_t dst_pitch);
 int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const rdfe_track_params &p,
               const double *d_curr_xy, double *d_next_xy, const int *d_counts, int stride, char *d_status);

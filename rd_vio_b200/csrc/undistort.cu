@@ -67,12 +67,69 @@ ingest_kernel(const uint8_t *const *__restrict__ src, size_t src_pitch, const ui
     else for (int i = 0; x + i < W; ++i) d[i] = (uint8_t)(out >> (8 * i));
 }
 
-int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t src_pitch, uint8_t *const *d_dst,
+// Gray frames with 4-byte aligned rows and W % 4 == 0 (the usual case): same arithmetic, fewer instructions.  A thread
+// still owns 4 adjacent output pixels; their map entries come as one 16-byte and one 8-byte load.  Per pixel the two
+// source rows are read as aligned 32-bit words (a second word only when the 2-pixel footprint straddles a word
+// boundary) and re-aligned with a funnel shift, so that (p00, p01) and (p10, p11) are the low byte pairs of two
+// registers; the blend is then two dp2a against the four 10-bit weight products:
+//   ((p00 wx0 + p01 wx1) wy0 + (p10 wx0 + p11 wx1) wy1) * 32 + 2^14 >> 15  ==  (sum_k p_k w_k + 512) >> 10   (integers).
+// A footprint that touches the image border takes the tap-by-tap BORDER_CONSTANT path of the general kernel.
+__global__ void __launch_bounds__(256)
+undistort_gray_fast_kernel(const uint8_t *const *__restrict__ src, size_t src_pitch, const uint32_t *__restrict__ map_xy,
+                           const uint16_t *__restrict__ map_f, uint8_t *const *__restrict__ dst, size_t dst_pitch, int W, int H) {
+    const int groups = W >> 2;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups * H) return;
+    const int y = g / groups, x = (g - y * groups) << 2;
+    const uint8_t *img = src[blockIdx.y];
+    const size_t o = (size_t)y * W + x;                                  // multiple of 4
+    const uint4 m4 = __ldg(reinterpret_cast<const uint4 *>(map_xy + o));
+    const uint2 f2 = __ldg(reinterpret_cast<const uint2 *>(map_f + o));
+    const unsigned ms[4] = {m4.x, m4.y, m4.z, m4.w};
+    const unsigned fs[4] = {f2.x & 0xFFFFu, f2.x >> 16, f2.y & 0xFFFFu, f2.y >> 16};
+    unsigned out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int sx = (int)(short)(ms[i] & 0xFFFFu), sy = (int)ms[i] >> 16;
+        const unsigned wx1 = fs[i] & 31u, wx0 = 32u - wx1, wy1 = fs[i] >> 5, wy0 = 32u - wy1;
+        const unsigned wt = (wx0 * wy0) | ((wx1 * wy0) << 16), wb = (wx0 * wy1) | ((wx1 * wy1) << 16);
+        unsigned top, bot;                                               // low two bytes: (p00, p01) / (p10, p11)
+        if ((unsigned)sx < (unsigned)(W - 1) && (unsigned)sy < (unsigned)(H - 1)) {
+            const unsigned sh = ((unsigned)sx & 3u) * 8u;
+            const uint8_t *r0 = img + (size_t)sy * src_pitch + (size_t)(sx & ~3);
+            const uint8_t *r1 = r0 + src_pitch;
+            const unsigned t0 = __ldg(reinterpret_cast<const unsigned *>(r0)), b0 = __ldg(reinterpret_cast<const unsigned *>(r1));
+            unsigned t1 = 0u, b1 = 0u;
+            if (sh == 24u) { t1 = __ldg(reinterpret_cast<const unsigned *>(r0 + 4)); b1 = __ldg(reinterpret_cast<const unsigned *>(r1 + 4)); }
+            top = __funnelshift_r(t0, t1, sh);
+            bot = __funnelshift_r(b0, b1, sh);
+        } else {
+            const bool x0 = (unsigned)sx < (unsigned)W, x1 = (unsigned)(sx + 1) < (unsigned)W;
+            const bool y0 = (unsigned)sy < (unsigned)H, y1 = (unsigned)(sy + 1) < (unsigned)H;
+            const uint8_t *r0 = img + (ptrdiff_t)sy * (ptrdiff_t)src_pitch + sx;
+            const uint8_t *r1 = r0 + src_pitch;
+            const unsigned p00 = (y0 && x0) ? __ldg(r0) : 0u, p01 = (y0 && x1) ? __ldg(r0 + 1) : 0u;
+            const unsigned p10 = (y1 && x0) ? __ldg(r1) : 0u, p11 = (y1 && x1) ? __ldg(r1 + 1) : 0u;
+            top = p00 | (p01 << 8);
+            bot = p10 | (p11 << 8);
+        }
+        const unsigned acc = __dp2a_lo(wb, bot, __dp2a_lo(wt, top, 512u));
+        out |= min(acc >> 10, 255u) << (8 * i);
+    }
+    *reinterpret_cast<unsigned *>(dst[blockIdx.y] + (size_t)y * dst_pitch + x) = out;
+}
+
+int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t src_pitch, int src_vec4, uint8_t *const *d_dst,
                      size_t dst_pitch) {
     const int W = ctx->cfg.width, H = ctx->cfg.height;
     const int groups = (W + 3) >> 2;
     dim3 grid((groups * H + 255) / 256, n);
     const int ch = ctx->in_channels;
+    if (ctx->und_on && ch == 1 && src_vec4 && W % 4 == 0 && dst_pitch % 4 == 0) {
+        RDFE_LAUNCH(ctx, K_UNDISTORT, (undistort_gray_fast_kernel<<<grid, 256, 0, ctx->ls>>>(d_src, src_pitch, ctx->und_map_xy, ctx->und_map_f,
+                                                                                           d_dst, dst_pitch, W, H)));
+        return 1;
+    }
 #define RDFE_INGEST(CH, UND)                                                                                            \
     RDFE_LAUNCH(ctx, K_UNDISTORT, (ingest_kernel<CH, UND><<<grid, 256, 0, ctx->ls>>>(d_src, src_pitch, ctx->und_map_xy,  \
                                                                                    ctx->und_map_f, d_dst, dst_pitch, W, H)))
