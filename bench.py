@@ -110,7 +110,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
-def run_cpu(args, wl, stream_ids, steps, warmup, budget_s=None):
+def run_cpu(args, wl, stream_ids, steps, warmup, budget_s=None, single_stream=False):
     """Times the reference's CPU path (oracle/) on all host cores. Returns dict."""
     from oracle.cpu_frontend import CpuFrontEndPool, pick_backend
     backend = pick_backend()
@@ -126,7 +126,12 @@ def run_cpu(args, wl, stream_ids, steps, warmup, budget_s=None):
             if budget_s and time.perf_counter() - t_begin > budget_s and len(times) >= 2:
                 break
         total = float(np.sum(times))
-        return {"value": len(stream_ids) * len(times) / total, "unit": UNIT, "cores": pool.workers,
+        single = None
+        if single_stream:
+            pool.close()      # free the cores before timing one stream alone
+            from oracle.cpu_frontend import single_stream_latency
+            single = single_stream_latency(wl, args.ring)
+        return {"value": len(stream_ids) * len(times) / total, "unit": UNIT, "cores": pool.workers, "single_stream": single,
                 "kind": "reference" if backend == "cv2" else "port",
                 "sample": f"{len(times)} steps x {len(stream_ids)} streams = {len(times) * len(stream_ids)} frames of the same "
                           f"synthetic workload, {pool.workers} worker processes x 1 OpenCV thread "
@@ -142,13 +147,13 @@ def main_reference(args, wl):
         return 0
     stream_ids = list(range(args.streams))
     WL.ensure_rings(stream_ids, wl["width"], wl["height"], args.ring)
-    res = run_cpu(args, wl, stream_ids, args.steps, max(args.warmup, 1), budget_s=150.0)
+    res = run_cpu(args, wl, stream_ids, args.steps, max(args.warmup, 1), budget_s=150.0, single_stream=True)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": res["steps"], "warmup": max(args.warmup, 1), "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
         "config": workload_config(args, wl, 1),
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "single_stream")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -145,3 +145,27 @@ class CpuFrontEndPool:
             p.join(timeout=5)
             if p.is_alive():
                 p.kill()
+
+
+def single_stream_latency(wl, ring, frames=60, stream_id=0):
+    """BASELINE configs[0]: ONE stream through the reference's call sequence on the host, per-frame latency with one
+    OpenCV thread and with OpenCV's default thread pool (cv2 backend only).  Median over `frames` frames."""
+    from .cv2_reference import HAVE_CV2
+    if not HAVE_CV2:
+        return None
+    import cv2
+    st = _StreamState(stream_id, wl, ring, "cv2")
+    out = {}
+    for label, nthreads in (("ms_per_frame_1_thread", 1), ("ms_per_frame_all_threads", -1)):
+        cv2.setNumThreads(nthreads)
+        if nthreads < 0:
+            out["opencv_threads"] = int(cv2.getNumThreads())
+        ts = []
+        for t in range(frames + 3):
+            t0 = time.perf_counter()
+            st.step(t)
+            ts.append(time.perf_counter() - t0)
+        out[label] = 1e3 * float(np.median(ts[3:]))
+    cv2.setNumThreads(-1)
+    return out
+

@@ -25,5 +25,8 @@ def test_reference_arm_line():
     assert d["value"] > 0 and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == pytest.approx(d["value"])
+    ss = cb["single_stream"]          # BASELINE configs[0]: one stream, per-frame latency on the host (cv2 backend only)
+    if cb["kind"] == "reference":
+        assert ss["ms_per_frame_1_thread"] > 0 and ss["ms_per_frame_all_threads"] > 0 and ss["opencv_threads"] >= 1
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0 and e["value"] == pytest.approx(d["value"])
