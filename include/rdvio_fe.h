@@ -213,8 +213,20 @@ RDFE_API int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy,
  * 3 = (level 0 only) the undistorted frame before CLAHE, if rdfe_set_undistort is active (w*h bytes). */
 RDFE_API int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst, size_t dst_bytes);
 RDFE_API int rdfe_download_clahe_lut(rdfe_ctx *ctx, int batch_index, uint8_t *dst, size_t dst_bytes);
+/* Inverse of plane 2: overwrite level 0 of a slot (the CLAHE output) with a caller-made image INCLUDING its win-px
+ * REFLECT_101 halo ((w+2win)*(h+2win) bytes), so that the detection stage can be tested on arbitrary level-0 content. */
+RDFE_API int rdfe_upload_level0(rdfe_ctx *ctx, int slot, const uint8_t *image_with_halo, size_t src_bytes);
 /* Harris response map of the slot's level-0 image (w*h floats). */
 RDFE_API int rdfe_harris_response(rdfe_ctx *ctx, int slot, const rdfe_detect_params *p, float *dst, size_t dst_bytes);
+/* What the Harris stage of the hot path hands to the selection: 64-bit keys (float bits of the response << 32 | y*w+x)
+ * of every positive 3x3 local maximum off the 1-px frame (goodFeaturesToTrack's candidates before its threshold), in
+ * no particular order, the frame maximum of the response, and the number of pixels the integer prefilter flagged for
+ * exact evaluation (0 when the exact-everywhere kernel ran: environment RDFE_HARRIS_EXACT=1). */
+RDFE_API int rdfe_harris_candidates(rdfe_ctx *ctx, int slot, const rdfe_detect_params *p, uint64_t *keys, size_t cap,
+                           unsigned *count, float *frame_max, unsigned *flagged);
+/* Constants of the prefilter's error bound eps(T) = T * (c1 * sqrt(T) + c2 * T) + rho_u and the degenerate-frame
+ * threshold rho_s (csrc/harris_exact.cuh): out[4] = {c1, c2, rho_u, rho_s}.  Needs no GPU. */
+RDFE_API void rdfe_harris_prefilter_constants(float *out);
 
 /* ---- device-buffer helpers for callers without a CUDA runtime binding --- */
 RDFE_API int rdfe_dev_alloc(rdfe_ctx *ctx, size_t bytes, void **dev_ptr);

@@ -64,7 +64,11 @@ SYMBOLS = {
     "rdfe_frontend_step_wait": (_i, [_vp, _i, _vp, _vp, _vp]),
     "rdfe_download_level": (_i, [_vp, _i, _i, _i, _vp, _sz]),
     "rdfe_download_clahe_lut": (_i, [_vp, _i, _vp, _sz]),
+    "rdfe_upload_level0": (_i, [_vp, _i, _vp, _sz]),
     "rdfe_harris_response": (_i, [_vp, _i, C.POINTER(DetectParams), _vp, _sz]),
+    "rdfe_harris_candidates": (_i, [_vp, _i, C.POINTER(DetectParams), _vp, _sz, C.POINTER(C.c_uint), C.POINTER(C.c_float),
+                                    C.POINTER(C.c_uint)]),
+    "rdfe_harris_prefilter_constants": (None, [C.POINTER(C.c_float)]),
     "rdfe_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "rdfe_dev_free": (_i, [_vp, _vp]),
     "rdfe_host_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),

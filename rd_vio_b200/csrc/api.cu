@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "fe_internal.cuh"
+#include "harris_exact.cuh"
 
 namespace rdfe {
 
@@ -312,6 +313,7 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->det.cand2, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->det.cand_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
+    CK(cudaMalloc(&ctx->det.flag_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.overflow, sizeof(unsigned)));
     CK(cudaMemset(ctx->det.overflow, 0, sizeof(unsigned)));
     ctx->det2 = ctx->det;
@@ -319,6 +321,7 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->det2.cand2, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->det2.cand_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det2.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
+    CK(cudaMalloc(&ctx->det2.flag_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     const size_t npts = (size_t)RDFE_MAX_BATCH * cfg->max_points;
     CK(cudaMalloc(&ctx->d_xy_a, npts * 2 * sizeof(double)));
     CK(cudaMalloc(&ctx->d_xy_b, npts * 2 * sizeof(double)));
@@ -404,8 +407,8 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int l = 0; l < RDFE_MAX_LEVELS; ++l) { cudaFree(ctx->pyr.img[l]); cudaFree(ctx->pyr.der[l]); }
     cudaFree(ctx->raw); cudaFree(ctx->lut); cudaFree(ctx->und_map_xy); cudaFree(ctx->und_map_f); cudaFree(ctx->und_plane);
-    cudaFree(ctx->det.cand); cudaFree(ctx->det.cand2); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.overflow);
-    if (ctx->det2.cand != ctx->det.cand) { cudaFree(ctx->det2.cand); cudaFree(ctx->det2.cand2); cudaFree(ctx->det2.cand_count); cudaFree(ctx->det2.frame_max); }
+    cudaFree(ctx->det.cand); cudaFree(ctx->det.cand2); cudaFree(ctx->det.cand_count); cudaFree(ctx->det.frame_max); cudaFree(ctx->det.flag_count); cudaFree(ctx->det.overflow);
+    if (ctx->det2.cand != ctx->det.cand) { cudaFree(ctx->det2.cand); cudaFree(ctx->det2.cand2); cudaFree(ctx->det2.cand_count); cudaFree(ctx->det2.frame_max); cudaFree(ctx->det2.flag_count); }
     cudaFree(ctx->d_xy_a); cudaFree(ctx->d_xy_b); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->d_gftt_xy); cudaFree(ctx->d_gftt_resp); cudaFree(ctx->d_gftt_counts); cudaFree(ctx->d_srcptrs);
     if (ctx->prof_ev) {
@@ -595,7 +598,7 @@ int rdfe_detect_prefetch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_dete
     ctx->det = ctx->det2;
     ctx->ls = ax;
     rc = check_launch(ctx, launch_harris_candidates(ctx, sl, *p, nullptr), "harris");
-    if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, ax, n, *p, ctx->pf_gftt_xy, ctx->pf_gftt_resp, ctx->pf_gftt_counts), "select");
+    if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, sl, *p, ctx->pf_gftt_xy, ctx->pf_gftt_resp, ctx->pf_gftt_counts), "select");
     ctx->det = det_keep;
     ctx->ls = ctx->stream;
     if (rc) return rc;
@@ -779,7 +782,7 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
             cudaStreamWaitEvent(ss, ctx->ev_harris_done[par], 0);
             cudaStreamWaitEvent(ss, ctx->ev_step_done[par], 0);   // poisson(s-2) has read this parity's gftt output
             ctx->ls = ss;
-            rc = check_launch(ctx, launch_gftt_select(ctx, ss, n, *dp, gxy, gre, gcn), "select");
+            rc = check_launch(ctx, launch_gftt_select(ctx, sn, *dp, gxy, gre, gcn), "select");
             cudaEventRecord(evj, ss);
         }
         ctx->det = det_keep;
@@ -834,7 +837,7 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         ctx->ls = axs;
     }
     rc = check_launch(ctx, launch_harris_candidates(ctx, sn, *dp, nullptr), "harris");
-    if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, ctx->ls, n, *dp, gxy, gre, gcn), "select");
+    if (rc == RDFE_OK) rc = check_launch(ctx, launch_gftt_select(ctx, sn, *dp, gxy, gre, gcn), "select");
     if (rc) { restore(); return rc; }
     if (ov) cudaEventRecord(evj, axs);
     // ---- tracking branch: pyramid levels + Scharr (still on the preprocess stream), then LK on the main stream
@@ -1019,6 +1022,23 @@ int rdfe_download_level(rdfe_ctx *ctx, int slot, int level, int plane, void *dst
     return RDFE_OK;
 }
 
+int rdfe_upload_level0(rdfe_ctx *ctx, int slot, const uint8_t *image_with_halo, size_t src_bytes) {
+    if (!ctx || !image_with_halo || slot < 0 || slot >= ctx->cfg.num_slots || !ctx->slot_used[slot]) {
+        set_error("rdfe_upload_level0: bad slot or null image");
+        return RDFE_ERR_INVALID;
+    }
+    const LevelGeom &g = ctx->pyr.lv[0];
+    const int win = ctx->pyr.win;
+    const size_t fw = (size_t)g.w + 2 * win, fh = (size_t)g.h + 2 * win;
+    if (src_bytes < fw * fh) { set_error("rdfe_upload_level0: buffer too small"); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    { const int rc_all = sync_all_streams(ctx); if (rc_all) return rc_all; }
+    ctx->pf_valid = false;
+    uint8_t *dst = ctx->pyr.image_origin(0, slot) - (size_t)win * g.ipitch - win;
+    RDFE_CUDA_OK(cudaMemcpy2D(dst, g.ipitch, image_with_halo, fw, fw, fh, cudaMemcpyHostToDevice));
+    return RDFE_OK;
+}
+
 int rdfe_download_clahe_lut(rdfe_ctx *ctx, int batch_index, uint8_t *dst, size_t dst_bytes) {
     if (!ctx || !dst || batch_index < 0 || batch_index >= RDFE_MAX_BATCH || ctx->last_clahe_tiles <= 0) {
         set_error("rdfe_download_clahe_lut: bad argument or no preprocess yet");
@@ -1049,6 +1069,33 @@ int rdfe_harris_response(rdfe_ctx *ctx, int slot, const rdfe_detect_params *p, f
     }
     cudaFree(d);
     return rc;
+}
+
+int rdfe_harris_candidates(rdfe_ctx *ctx, int slot, const rdfe_detect_params *p, uint64_t *keys, size_t cap, unsigned *count,
+                           float *frame_max, unsigned *flagged) {
+    SlotList sl;
+    int rc = check_slots(ctx, &slot, 1, &sl, "rdfe_harris_candidates");
+    if (rc) return rc;
+    if (!p || !keys || !count || !frame_max) { set_error("rdfe_harris_candidates: null argument"); return RDFE_ERR_INVALID; }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    rc = check_launch(ctx, launch_harris_candidates(ctx, sl, *p, nullptr), "harris");
+    if (rc) return rc;
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    unsigned n = 0, fm = 0, nf = 0;
+    RDFE_CUDA_OK(cudaMemcpy(&n, ctx->det.cand_count, sizeof n, cudaMemcpyDeviceToHost));
+    RDFE_CUDA_OK(cudaMemcpy(&fm, ctx->det.frame_max, sizeof fm, cudaMemcpyDeviceToHost));
+    RDFE_CUDA_OK(cudaMemcpy(&nf, ctx->det.flag_count, sizeof nf, cudaMemcpyDeviceToHost));
+    if (n > ctx->det.cand_cap || n > cap) { set_error("rdfe_harris_candidates: %u candidates exceed the capacity", n); return RDFE_ERR_OVERFLOW; }
+    RDFE_CUDA_OK(cudaMemcpy(keys, ctx->det.cand, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *count = n;
+    memcpy(frame_max, &fm, sizeof fm);
+    if (flagged) *flagged = nf;
+    return RDFE_OK;
+}
+
+void rdfe_harris_prefilter_constants(float *out) {
+    if (!out) return;
+    out[0] = rdfe::kHarrisC1; out[1] = rdfe::kHarrisC2; out[2] = rdfe::kHarrisRhoU; out[3] = rdfe::kHarrisRhoS;
 }
 
 // ---------------------------------------------------------- memory helpers
@@ -1091,7 +1138,8 @@ int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t b
 }
 
 static const char *const kKernelNames[K_COUNT] = {"clahe_hist_lut", "clahe_apply", "pyrdown", "scharr",
-                                                  "harris_nms", "select", "lk_track", "poisson_append", "undistort"};
+                                                  "harris_nms", "select", "lk_track", "poisson_append", "undistort",
+                                                  "harris_resolve"};
 
 int rdfe_profile_num_kernels(void) { return K_COUNT; }
 const char *rdfe_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }

@@ -149,7 +149,7 @@ inline int adaptive_strip_rows(int height, int warps_per_row_strip, int min_rows
 }
 
 enum KernelId {
-    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_COUNT
+    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_HARRIS_RESOLVE, K_COUNT
 };
 constexpr int kProfMax = 4096;      // timed launches between two rdfe_profile_collect calls
 
@@ -159,6 +159,7 @@ struct DetectScratch {
     unsigned *cand_count;         // [RDFE_MAX_BATCH]
     unsigned *frame_max;          // [RDFE_MAX_BATCH] max response bits (responses <= 0 never win)
     unsigned *overflow;           // [1]
+    unsigned *flag_count;         // [RDFE_MAX_BATCH] pixels flagged by the Harris prefilter (list: cand2 viewed as 32-bit entries)
     unsigned cand_cap;
 };
 
@@ -287,7 +288,7 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
                              float *d_response /* optional [n][H][W] */);
 int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, double *d_xy, int *d_counts,
                   int stride, float *d_gftt_xy, float *d_gftt_resp, int *d_gftt_counts);
-int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_detect_params &p, float *d_gftt_xy,
+int launch_gftt_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_gftt_xy,
                        float *d_gftt_resp, int *d_gftt_counts);
 int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, const float *d_gftt_xy,
                           const int *d_gftt_counts, double *d_xy, int *d_counts, int stride);

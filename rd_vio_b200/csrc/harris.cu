@@ -17,6 +17,7 @@
 // select kernel applies thr.  The response map itself never goes to HBM on the hot path.
 #include <cstdlib>
 #include "fe_internal.cuh"
+#include "harris_exact.cuh"
 
 namespace rdfe {
 
@@ -38,6 +39,7 @@ constexpr int HR_ROWS = 80;            // output rows per warp strip at full bat
 constexpr int HR_COLS = 120;           // output columns per warp (lanes 1..30)
 constexpr int HW_WARPS = 4;            // warps per CTA
 constexpr int HW_BUF = 256;            // per-warp candidate staging (keys)
+constexpr int HW_FBUF = 384;           // per-warp flag staging of the prefilter path (32-bit entries)
 
 __device__ __forceinline__ float byte_f(unsigned w, int k) {
     // byte k of w as float: build 2^23 + b by PRMT, subtract 2^23 (exact)
@@ -284,6 +286,285 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
     }
 }
 
+// =====================================================================================================================
+// Prefilter path (default): the float64 chain above costs ~90 instructions per pixel although < 3 % of the pixels can
+// be local maxima.  harris_flag_kernel evaluates, for ALL pixels, the integer Sobel gradients (IDP.4A on the pixel
+// bytes), their products and 3x3 box sums (exact, < 2^24) and an interval [lo, hi] = Ru -+ eps(T) that provably
+// contains the reference's float32 response divided by sigma^4 (harris_exact.cuh), and flags a pixel iff it may be a
+// positive 3x3 local maximum (hi >= max of the neighbours' lo); the flag carries a "certain" bit when it surely is one
+// (lo > max of the neighbours' hi).  harris_resolve_kernel then evaluates the reference's exact arithmetic at the
+// flagged pixels only (and, for uncertain ones, at their 8 neighbours), emits the same 64-bit keys as the exact
+// kernel and the exact frame maximum (the maximum pixel is always flagged).  Same strips, lane groups and halo reads
+// as harris_strip.
+__device__ __forceinline__ int dp4a_u8s8(unsigned px, int w, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(w), "r"(c));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float sqrt_approx(float a) {
+    float d;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(a));   // T is 0 or >= 1: flushing subnormals changes nothing
+    return d;
+}
+
+template <int V> struct IntC { static constexpr int value = V; };
+
+// Blackwell packed float32 pairs (FADD2 / FMUL2 / FFMA2): two lanes per instruction on the fma pipe
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+
+// The loop body is unrolled three times over rings of three registers per history (products of the last rows, the
+// -s row terms, the interval rows), indexed at compile time, so that no register is ever moved.
+template <bool BORDER>
+__device__ __forceinline__ void harris_flag_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0w, int hr_rows,
+                                                  int gl_lanes, int n_groups, const DetectScratch &det, int b, unsigned *buf, unsigned *cnt) {
+    const int lane = threadIdx.x & 31;
+    const int GL = BORDER ? gl_lanes : 32;
+    const int grp = BORDER ? lane / GL : 0;
+    const int gl = lane - grp * GL;
+    const int y0 = y0w + grp * hr_rows;
+    const bool active = !BORDER || (grp < n_groups && y0 < H);
+    const int c0 = x0 - 4 + 4 * gl;
+    const bool ld_ok = BORDER ? (active && (c0 + 3 <= W + 20) && (c0 >= -20)) : true;
+    const bool out_lane = active && gl >= 1 && gl <= GL - 2;
+    bool bflipx[4];
+    float cinv[4];                                          // 0 or -inf: column outside the image
+    unsigned colmask = 0;                                   // columns of this lane that may be flagged
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = c0 + i;
+        const bool outside = BORDER && (x < 0 || x >= W);
+        bflipx[i] = outside;
+        cinv[i] = outside ? -INFINITY : 0.0f;
+        if (out_lane && !outside) colmask |= 1u << i;
+    }
+    // weights of the row filters on bytes (x-1, x, x+1, -): [-1 0 1], 2 * [-1 0 1], [1 2 1], -[1 2 1]
+    constexpr int WD = 0x000100FF, WD2 = 0x000200FE, WS = 0x00010201, WSN = 0x00FFFEFF;
+    int P[4] = {0, 0, 0, 0}, dprev[4] = {0, 0, 0, 0};       // d(y-2) + 2 d(y-1), d(y-1)
+    int ns[3][4], pa[3][4], pb[3][4], pc[3][4];             // rings: -s of the last rows, products of the last rows
+    float L[3][6], Hh[3][6];                                // rings: interval rows (columns -1 .. 4)
+    float Lx[3][4], Hx[3][4];                               // rings: horizontal max3 of the interval rows
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ns[r][i] = 0; pa[r][i] = 0; pb[r][i] = 0; pc[r][i] = 0; Lx[r][i] = -INFINITY; Hx[r][i] = -INFINITY; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { L[r][i] = -INFINITY; Hh[r][i] = -INFINITY; }
+    }
+
+    unsigned nstaged = 0;
+    unsigned *list = reinterpret_cast<unsigned *>(det.cand2 + (size_t)b * det.cand_cap);   // 2 * cand_cap = W * H entries: cannot overflow
+    auto flush = [&]() {
+        const unsigned nb = nstaged;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&det.flag_count[b], nb);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (unsigned i = lane; i < nb; i += 32) list[base + i] = buf[i];
+        __syncwarp();
+        if (lane == 0) *cnt = 0u;
+        nstaged = 0;
+        __syncwarp();
+    };
+
+    const int rows = active ? min(hr_rows, H - y0) : 0;
+    const int steps = min(hr_rows, H - y0w) + 6;
+    const int my_steps = BORDER ? rows + 6 : steps;
+    const uint8_t *rowp = org + (ptrdiff_t)(y0 - 3) * ipitch + c0;
+    unsigned wq0 = 0, wq1 = 0;
+    if (ld_ok) { wq0 = *reinterpret_cast<const unsigned *>(rowp); wq1 = *reinterpret_cast<const unsigned *>(rowp + ipitch); }
+    rowp += 2 * (ptrdiff_t)ipitch;
+    unsigned addr_row = (unsigned)((y0 - 6) * W + c0);       // pixel address of (row n = y0-6+j, column c0)
+
+    // one pixel row: PH = j % 3 selects the ring slots
+    auto step = [&](auto ph, int j) {
+        constexpr int R0 = decltype(ph)::value, R1 = (R0 + 1) % 3, R2 = (R0 + 2) % 3;   // R0: written now; R1: oldest; R2: previous
+        const unsigned w = wq0;
+        wq0 = wq1;
+        if (ld_ok && j + 2 < my_steps) wq1 = *reinterpret_cast<const unsigned *>(rowp);
+        rowp += ipitch;
+        const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+        unsigned al[4];                                      // bytes (x-1, x, x+1, x+2) of column x = c0 + i
+        al[0] = __funnelshift_r(wl, w, 24);
+        al[1] = w;
+        al[2] = __funnelshift_r(w, wr, 8);
+        al[3] = __funnelshift_r(w, wr, 16);
+        // ---- integer Sobel of centre row pr = y-1 (rows y-2, y-1, y), products, vertical 3-sums of row q = pr-1
+        const int pr = y0 - 4 + j;
+        const bool bflipy = BORDER && ((pr < 0) || (pr >= H));
+        int va[6], vb[6], vc[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gx = dp4a_u8s8(al[i], WD, P[i]);
+            const int gy = dp4a_u8s8(al[i], WS, ns[R1][i]);   // s(y) - s(y-2)
+            P[i] = dp4a_u8s8(al[i], WD2, dprev[i]);
+            dprev[i] = dp4a_u8s8(al[i], WD, 0);
+            ns[R0][i] = dp4a_u8s8(al[i], WSN, 0);             // slot R0 held -s(y-3): dead
+            int nb = gx * gy;
+            if (BORDER && (bflipx[i] != bflipy)) nb = -nb;   // the product of a mirrored row or column changes sign
+            pa[R0][i] = gx * gx; pb[R0][i] = nb; pc[R0][i] = gy * gy;
+            va[i + 1] = pa[R1][i] + pa[R2][i] + pa[R0][i];
+            vb[i + 1] = pb[R1][i] + pb[R2][i] + pb[R0][i];
+            vc[i + 1] = pc[R1][i] + pc[R2][i] + pc[R0][i];
+        }
+        va[0] = __shfl_up_sync(0xffffffffu, va[4], 1); vb[0] = __shfl_up_sync(0xffffffffu, vb[4], 1); vc[0] = __shfl_up_sync(0xffffffffu, vc[4], 1);
+        va[5] = __shfl_down_sync(0xffffffffu, va[1], 1); vb[5] = __shfl_down_sync(0xffffffffu, vb[1], 1); vc[5] = __shfl_down_sync(0xffffffffu, vc[1], 1);
+        // ---- interval of the response of row q (ring slot R0), two pixels per instruction
+        const int q = pr - 1;
+        const float rinv = (BORDER && (q < 0 || q >= H)) ? -INFINITY : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+            const F2 fA = f2_pack((float)(va[i] + va[i + 1] + va[i + 2]), (float)(va[i + 1] + va[i + 2] + va[i + 3]));
+            const F2 nB = f2_pack((float)(vb[i] + vb[i + 1] + vb[i + 2]), (float)(vb[i + 1] + vb[i + 2] + vb[i + 3]));   // -IB (products stored negated)
+            const F2 fC = f2_pack((float)(vc[i] + vc[i + 1] + vc[i + 2]), (float)(vc[i + 1] + vc[i + 2] + vc[i + 3]));
+            const F2 T = f2_add(fA, fC);
+            // ru = IA*IC - IB^2 - 0.04 T^2 = -(nB*nB) ... evaluated as fma(T, -0.04 T, fma(nB, -nB, IA*IC)): the sign of IB drops out,
+            // so a second register with the negated sum is avoided by squaring through (nB * kNeg) * nB
+            const F2 kNeg = f2_pack(-1.0f, -1.0f), kK = f2_pack(-0.04f, -0.04f);
+            F2 ru = f2_fma(f2_mul(nB, kNeg), nB, f2_mul(fA, fC));
+            ru = f2_fma(f2_mul(T, kK), T, ru);
+            float t0, t1;
+            f2_unpack(T, t0, t1);
+            const F2 sq = f2_pack(sqrt_approx(t0), sqrt_approx(t1));
+            const F2 e = f2_fma(T, f2_fma(f2_pack(kHarrisC1, kHarrisC1), sq, f2_mul(f2_pack(kHarrisC2, kHarrisC2), T)), f2_pack(kHarrisRhoU, kHarrisRhoU));
+            F2 lo = f2_fma(e, kNeg, ru), hi = f2_add(ru, e);
+            if (BORDER) {
+                const F2 off = f2_pack(cinv[i] + rinv, cinv[i + 1] + rinv);   // -inf outside the image (dilate ignores those pixels)
+                lo = f2_add(lo, off); hi = f2_add(hi, off);
+            }
+            f2_unpack(lo, L[R0][i + 1], L[R0][i + 2]);
+            f2_unpack(hi, Hh[R0][i + 1], Hh[R0][i + 2]);
+        }
+        L[R0][0] = __shfl_up_sync(0xffffffffu, L[R0][4], 1); Hh[R0][0] = __shfl_up_sync(0xffffffffu, Hh[R0][4], 1);
+        L[R0][5] = __shfl_down_sync(0xffffffffu, L[R0][1], 1); Hh[R0][5] = __shfl_down_sync(0xffffffffu, Hh[R0][1], 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { Lx[R0][i] = fmax3(L[R0][i], L[R0][i + 1], L[R0][i + 2]); Hx[R0][i] = fmax3(Hh[R0][i], Hh[R0][i + 1], Hh[R0][i + 2]); }
+        // ---- NMS of row n = q-1 (ring slot R2) on the intervals: rows n-1 (slot R1, max3), n, n+1 (slot R0, max3)
+        const int n = q - 1;
+        if (j >= 6) {
+            // flagged <=> hi >= max(neighbours' lo, rho+) (rho+ = next float above kHarrisRhoU turns "hi > rho" into ">=");
+            // certain <=> lo > max(neighbours' hi)
+            const float rho_next = __uint_as_float(__float_as_uint(kHarrisRhoU) + 1u);
+            bool fl[4], ce[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float mlo = fmax3(fmax3(L[R2][i], L[R2][i + 2], rho_next), Lx[R1][i], Lx[R0][i]);
+                const float mhi = fmax3(fmaxf(Hh[R2][i], Hh[R2][i + 2]), Hx[R1][i], Hx[R0][i]);
+                fl[i] = Hh[R2][i + 1] >= mlo;
+                ce[i] = L[R2][i + 1] > mhi;
+            }
+            unsigned fmask = (fl[0] ? 1u : 0u) | (fl[1] ? 2u : 0u) | (fl[2] ? 4u : 0u) | (fl[3] ? 8u : 0u);
+            const unsigned cmask = (ce[0] ? 1u : 0u) | (ce[1] ? 2u : 0u) | (ce[2] ? 4u : 0u) | (ce[3] ? 8u : 0u);
+            fmask &= (n < y0 + rows) ? colmask : 0u;         // n >= y0 >= 0 and y0 + rows <= H; apron lanes / columns outside the image never flag
+            const unsigned nmine = __popc(fmask);
+            if (nmine) {
+                unsigned pos = atomicAdd(cnt, nmine);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (fmask & (1u << i)) buf[pos] = (addr_row + (unsigned)i) | (((cmask >> i) & 1u) << 31);
+                    pos += (fmask >> i) & 1u;
+                }
+            }
+            nstaged += __reduce_add_sync(0xffffffffu, nmine);
+            if (nstaged > (unsigned)(HW_FBUF - 128)) flush();
+        }
+        addr_row += (unsigned)W;
+    };
+    const int steps3 = (steps + 2) / 3 * 3;                  // the up to 2 extra steps read nothing and flag nothing
+#pragma unroll 1
+    for (int j = 0; j < steps3; j += 3) {
+        step(IntC<0>{}, j);
+        step(IntC<1>{}, j + 1);
+        step(IntC<2>{}, j + 2);
+    }
+    if (nstaged) flush();
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(HW_WARPS * 32, MINB)
+harris_flag_kernel(Pyramid pyr, SlotList slots, DetectScratch det, int tiles_x, int strips, int gl_narrow, int n_items, int hr_rows) {
+    __shared__ unsigned s_buf[HW_WARPS][HW_FBUF];
+    __shared__ unsigned s_cnt[HW_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
+    const int total = n_items * slots.n;
+    for (int wi = blockIdx.x * HW_WARPS + warp; wi < total; wi += gridDim.x * HW_WARPS) {
+        const int b = wi / n_items, item = wi - b * n_items, slot = slots.v[b];
+        int x0, y0, gl_lanes = 32, n_groups = 1;
+        if (item < tiles_x * strips) { x0 = (item % tiles_x) * HR_COLS; y0 = (item / tiles_x) * hr_rows; }
+        else {
+            gl_lanes = gl_narrow; n_groups = gl_narrow == 10 ? 3 : 2;
+            x0 = tiles_x * HR_COLS; y0 = (item - tiles_x * strips) * n_groups * hr_rows;
+        }
+        const uint8_t *org = pyr.image_origin(0, slot);
+        if (lane == 0) s_cnt[warp] = 0u;
+        __syncwarp();
+        // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+hr_rows+2 all inside the image
+        const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
+        if (interior) harris_flag_strip<false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, det, b, s_buf[warp], &s_cnt[warp]);
+        else harris_flag_strip<true>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, det, b, s_buf[warp], &s_cnt[warp]);
+    }
+}
+
+// Exact response at the flagged pixels: 64-bit keys of the positive 3x3 local maxima off the 1-px frame (the
+// candidates of goodFeaturesToTrack before its threshold) and the frame maximum.
+constexpr int HV_THREADS = 256;
+template <bool kFma>
+__global__ void __launch_bounds__(HV_THREADS)
+harris_resolve_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
+    const uint8_t *org = pyr.image_origin(0, slots.v[b]);
+    const unsigned nflag = det.flag_count[b];
+    const unsigned *list = reinterpret_cast<const unsigned *>(det.cand2 + (size_t)b * det.cand_cap);
+    unsigned long long *out = det.cand + (size_t)b * det.cand_cap;
+    float tmax = 0.0f;
+    for (unsigned base = blockIdx.x * HV_THREADS; base < nflag; base += gridDim.x * HV_THREADS) {   // CTA-uniform
+        const unsigned i = base + threadIdx.x;
+        bool emit = false;
+        unsigned long long key = 0ull;
+        if (i < nflag) {
+            const unsigned e = list[i], addr = e & 0x7FFFFFFFu;
+            const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
+            const float v = harris_exact_at<kFma>(org, ipitch, W, H, x, y, k);
+            tmax = fmaxf(tmax, v);
+            if (v > 0.0f && x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+                bool ok = true;
+                if (!(e >> 31)) {                            // not certain: compare with the exact neighbours
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) {
+                        if (t == 4) continue;
+                        if (v < harris_exact_at<kFma>(org, ipitch, W, H, x + t % 3 - 1, y + t / 3 - 1, k)) ok = false;
+                    }
+                }
+                emit = ok;
+                key = ((unsigned long long)__float_as_uint(v) << 32) | addr;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if (m) {
+            unsigned pos = 0;
+            if (lane == 0) pos = atomicAdd(&det.cand_count[b], (unsigned)__popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+            if (emit) {
+                if (pos < det.cand_cap) out[pos] = key;
+                else atomicExch(det.overflow, 1u);
+            }
+        }
+    }
+    const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
+    if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
+}
+
 // Experiment switches (environment, read once): RDFE_HARRIS_ROWS = strip height at full batches, RDFE_HARRIS_NARROW=0
 // walks the narrow last tile one strip per warp like the full tiles.
 static int harris_max_rows() {
@@ -295,9 +576,14 @@ static bool harris_narrow_enabled() {
     return v;
 }
 
+static bool harris_prefilter_enabled() {
+    static const bool v = [] { const char *e = getenv("RDFE_HARRIS_EXACT"); return !(e && e[0] == '1'); }();
+    return v;
+}
+
 __global__ void detect_reset_kernel(DetectScratch det, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { det.cand_count[i] = 0u; det.frame_max[i] = 0u; }
+    if (i < n) { det.cand_count[i] = 0u; det.frame_max[i] = 0u; det.flag_count[i] = 0u; }
 }
 
 int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_response) {
@@ -314,6 +600,23 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
     const int n_items = tiles_x * strips + (gl_narrow ? (strips + n_groups - 1) / n_groups : 0);
     const int total = n_items * slots.n;
     dim3 grid((total + HW_WARPS - 1) / HW_WARPS);     // one warp per (image, strip); the kernel's loop also accepts fewer
+    if (!d_response && harris_prefilter_enabled()) {
+        // RDFE_HARRIS_MB=3: 153 registers, no spills, 12 warps per SM; 4 (default): 128 registers, 16 warps per SM
+        static const int minb = [] { const char *e = getenv("RDFE_HARRIS_MB"); return e ? atoi(e) : 4; }();
+        if (minb == 3)
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_flag_kernel<3><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        else
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_flag_kernel<4><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        // ~2.5 % of the pixels are flagged; a few CTAs per image walk the list
+        int gx = (kSMs * 8) / slots.n;
+        gx = gx < 8 ? 8 : gx > 96 ? 96 : gx;
+        dim3 g2(gx, slots.n);
+        if (p.harris_fma)
+            RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<true><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det)));
+        else
+            RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<false><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det)));
+        return 3;
+    }
     if (p.harris_fma)
         RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
     else

@@ -14,6 +14,7 @@
 //      reject iff squared distance < r^2; float64) against the caller's existing keypoints,
 //      then the 20-px border reject, then append.
 #include "fe_internal.cuh"
+#include "harris_exact.cuh"
 
 namespace rdfe {
 
@@ -32,6 +33,8 @@ struct SelectParams {
     int border;
     int stride;              // keypoint capacity per image
     int cap_k;               // accepted-corner capacity (= max_corners)
+    float harris_k;          // for the exact fallback of degenerate frames
+    int harris_fma, prefiltered;
 };
 
 __device__ __forceinline__ bool poisson_block_hit(int dcx, int dcy, int span) {
@@ -60,8 +63,8 @@ __device__ __forceinline__ bool grid_pass(const uint4 *cellpts, int gw, int gh, 
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, float *__restrict__ gftt_resp,
-              int *__restrict__ gftt_counts) {
+select_kernel(DetectScratch det, SelectParams sp, Pyramid pyr, SlotList slots, float *__restrict__ gftt_xy,
+              float *__restrict__ gftt_resp, int *__restrict__ gftt_counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *batch = reinterpret_cast<unsigned long long *>(smem_raw);          // [SEL_CAP]
     unsigned *hist = reinterpret_cast<unsigned *>(batch + SEL_CAP);                         // [256]
@@ -80,9 +83,21 @@ select_kernel(DetectScratch det, SelectParams sp, float *__restrict__ gftt_xy, f
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
-    const unsigned n = min(det.cand_count[b], det.cand_cap);
-    const float maxv = __uint_as_float(det.frame_max[b]);
-    const float thr = (float)((double)maxv * sp.quality);
+    unsigned n = min(det.cand_count[b], det.cand_cap);
+    float maxv = __uint_as_float(det.frame_max[b]);
+    float thr = (float)((double)maxv * sp.quality);
+    if (sp.prefiltered && thr < kHarrisRhoS) {
+        // Degenerate frame (no response above the rounding residue of vanishing integer gradients, e.g. a blank
+        // frame): the prefilter's candidate list is not trustworthy below kHarrisRhoS -- recompute the frame with the
+        // reference's exact arithmetic at every pixel (harris_exact.cuh).  CTA-uniform branch.
+        __shared__ unsigned s_fb_count, s_fb_max;
+        harris_exact_all(pyr.image_origin(0, slots.v[b]), pyr.lv[0].ipitch, sp.W, sp.H, sp.harris_k, sp.harris_fma != 0,
+                         reinterpret_cast<float *>(det.cand2 + (size_t)b * det.cand_cap), det.cand + (size_t)b * det.cand_cap,
+                         det.cand_cap, &s_fb_count, &s_fb_max, det.overflow);
+        n = min(s_fb_count, det.cand_cap);
+        maxv = __uint_as_float(s_fb_max);
+        thr = (float)((double)maxv * sp.quality);
+    }
     const unsigned thr_bits = __float_as_uint(thr);       // thr >= 0 here (maxv >= 0)
     const int W = sp.W;
 
@@ -526,11 +541,15 @@ static void fill_select_params(rdfe_ctx *ctx, const rdfe_detect_params &p, int s
     sp.border = p.border;
     sp.stride = stride;
     sp.cap_k = p.max_points;
+    sp.harris_k = (float)p.harris_k;
+    sp.harris_fma = p.harris_fma;
+    sp.prefiltered = 1;
 }
 
 // GFTT selection on `stream` (may be the context's auxiliary stream): candidates -> gftt_* arrays
-int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_detect_params &p, float *d_gftt_xy,
+int launch_gftt_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_gftt_xy,
                        float *d_gftt_resp, int *d_gftt_counts) {
+    const int n = slots.n;
     SelectParams sp;
     fill_select_params(ctx, p, 1, sp);
     const size_t smem = (size_t)SEL_CAP * 8 + 256 * 4 + (size_t)sp.cap_k * 12 + 16 + (size_t)sp.gw * sp.gh * 20 + 64;
@@ -547,8 +566,7 @@ int launch_gftt_select(rdfe_ctx *ctx, cudaStream_t stream, int n, const rdfe_det
         }
         s_attr = smem;
     }
-    (void)stream;
-    RDFE_LAUNCH(ctx, K_SELECT, (select_kernel<<<n, SEL_THREADS, smem, ctx->ls>>>(ctx->det, sp, d_gftt_xy, d_gftt_resp, d_gftt_counts)));
+    RDFE_LAUNCH(ctx, K_SELECT, (select_kernel<<<n, SEL_THREADS, smem, ctx->ls>>>(ctx->det, sp, ctx->pyr, slots, d_gftt_xy, d_gftt_resp, d_gftt_counts)));
     return 1;
 }
 
@@ -575,7 +593,7 @@ int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params
     float *gxy = d_gftt_xy ? d_gftt_xy : ctx->d_gftt_xy;
     float *gre = d_gftt_resp ? d_gftt_resp : ctx->d_gftt_resp;
     int *gcn = d_gftt_counts ? d_gftt_counts : ctx->d_gftt_counts;
-    int rc = launch_gftt_select(ctx, ctx->stream, slots.n, p, gxy, gre, gcn);
+    int rc = launch_gftt_select(ctx, slots, p, gxy, gre, gcn);
     if (rc < 0) return rc;
     if (!d_xy) return 1;
     rc = launch_poisson_append(ctx, slots.n, p, gxy, gcn, d_xy, d_counts, stride);

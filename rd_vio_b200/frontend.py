@@ -188,6 +188,14 @@ class FrontEnd:
         N.check(self._L.rdfe_download_level(self._h, slot, level, plane, _vp(out), out.nbytes), "rdfe_download_level")
         return out
 
+    def upload_level0(self, slot, image):
+        """Test tap: replace level 0 of `slot` (normally the CLAHE output) by `image` with its REFLECT_101 halo."""
+        img = np.ascontiguousarray(image, np.uint8)
+        if img.shape != (self.height, self.width):
+            raise ValueError(f"image shape {img.shape} != {(self.height, self.width)}")
+        padded = np.ascontiguousarray(np.pad(img, self.win, mode="reflect"))      # numpy 'reflect' == BORDER_REFLECT_101
+        N.check(self._L.rdfe_upload_level0(self._h, slot, _vp(padded), padded.nbytes), "rdfe_upload_level0")
+
     def download_clahe_lut(self, batch_index=0, tiles=64):
         out = np.empty((tiles, 256), np.uint8)
         N.check(self._L.rdfe_download_clahe_lut(self._h, batch_index, _vp(out), out.nbytes), "rdfe_download_clahe_lut")
@@ -198,6 +206,17 @@ class FrontEnd:
         p = self.detect_params(**params)
         N.check(self._L.rdfe_harris_response(self._h, slot, C.byref(p), _vp(out), out.nbytes), "rdfe_harris_response")
         return out
+
+    def harris_candidates(self, slot, **params):
+        """Keys (response bits << 32 | y*w+x) the Harris stage of the hot path emits, the frame maximum and the number of
+        pixels its prefilter flagged for exact evaluation: (keys uint64 sorted descending, frame_max, flagged)."""
+        cap = self.width * self.height // 2
+        keys = np.empty(cap, np.uint64)
+        n, fm, nf = C.c_uint(0), C.c_float(0.0), C.c_uint(0)
+        p = self.detect_params(**params)
+        N.check(self._L.rdfe_harris_candidates(self._h, slot, C.byref(p), _vp(keys), cap, C.byref(n), C.byref(fm), C.byref(nf)),
+                "rdfe_harris_candidates")
+        return np.sort(keys[:n.value])[::-1].copy(), float(fm.value), int(nf.value)
 
 
 class GpuImage:
