@@ -149,7 +149,7 @@ inline int adaptive_strip_rows(int height, int warps_per_row_strip, int min_rows
 }
 
 enum KernelId {
-    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_HARRIS_RESOLVE, K_COUNT
+    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_HARRIS_RESOLVE, K_HARRIS_COMPACT, K_COUNT
 };
 constexpr int kProfMax = 4096;      // timed launches between two rdfe_profile_collect calls
 

@@ -39,7 +39,6 @@ constexpr int HR_ROWS = 80;            // output rows per warp strip at full bat
 constexpr int HR_COLS = 120;           // output columns per warp (lanes 1..30)
 constexpr int HW_WARPS = 4;            // warps per CTA
 constexpr int HW_BUF = 256;            // per-warp candidate staging (keys)
-constexpr int HW_FBUF = 384;           // per-warp flag staging of the prefilter path (32-bit entries)
 
 __device__ __forceinline__ float byte_f(unsigned w, int k) {
     // byte k of w as float: build 2^23 + b by PRMT, subtract 2^23 (exact)
@@ -326,7 +325,7 @@ __device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2
 // -s row terms, the interval rows), indexed at compile time, so that no register is ever moved.
 template <bool BORDER>
 __device__ __forceinline__ void harris_flag_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0w, int hr_rows,
-                                                  int gl_lanes, int n_groups, const DetectScratch &det, int b, unsigned *buf, unsigned *cnt) {
+                                                  int gl_lanes, int n_groups, uint8_t *__restrict__ bm, int bm_pitch) {
     const int lane = threadIdx.x & 31;
     const int GL = BORDER ? gl_lanes : 32;
     const int grp = BORDER ? lane / GL : 0;
@@ -361,21 +360,6 @@ __device__ __forceinline__ void harris_flag_strip(const uint8_t *__restrict__ or
         for (int i = 0; i < 6; ++i) { L[r][i] = -INFINITY; Hh[r][i] = -INFINITY; }
     }
 
-    unsigned nstaged = 0;
-    unsigned *list = reinterpret_cast<unsigned *>(det.cand2 + (size_t)b * det.cand_cap);   // 2 * cand_cap = W * H entries: cannot overflow
-    auto flush = [&]() {
-        const unsigned nb = nstaged;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&det.flag_count[b], nb);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        __syncwarp();
-        for (unsigned i = lane; i < nb; i += 32) list[base + i] = buf[i];
-        __syncwarp();
-        if (lane == 0) *cnt = 0u;
-        nstaged = 0;
-        __syncwarp();
-    };
-
     const int rows = active ? min(hr_rows, H - y0) : 0;
     const int steps = min(hr_rows, H - y0w) + 6;
     const int my_steps = BORDER ? rows + 6 : steps;
@@ -383,7 +367,9 @@ __device__ __forceinline__ void harris_flag_strip(const uint8_t *__restrict__ or
     unsigned wq0 = 0, wq1 = 0;
     if (ld_ok) { wq0 = *reinterpret_cast<const unsigned *>(rowp); wq1 = *reinterpret_cast<const unsigned *>(rowp + ipitch); }
     rowp += 2 * (ptrdiff_t)ipitch;
-    unsigned addr_row = (unsigned)((y0 - 6) * W + c0);       // pixel address of (row n = y0-6+j, column c0)
+    // flag bytes: bits 0-3 = columns c0 .. c0+3 of row n may be positive local maxima, bits 4-7 = they surely are
+    uint8_t *bm_row = bm + (ptrdiff_t)(y0 - 6) * bm_pitch + (c0 >> 2);   // row n = y0-6+j
+    const bool st_ok = out_lane && c0 >= 0 && c0 < W;
 
     // one pixel row: PH = j % 3 selects the ring slots
     auto step = [&](auto ph, int j) {
@@ -464,20 +450,9 @@ __device__ __forceinline__ void harris_flag_strip(const uint8_t *__restrict__ or
             }
             unsigned fmask = (fl[0] ? 1u : 0u) | (fl[1] ? 2u : 0u) | (fl[2] ? 4u : 0u) | (fl[3] ? 8u : 0u);
             const unsigned cmask = (ce[0] ? 1u : 0u) | (ce[1] ? 2u : 0u) | (ce[2] ? 4u : 0u) | (ce[3] ? 8u : 0u);
-            fmask &= (n < y0 + rows) ? colmask : 0u;         // n >= y0 >= 0 and y0 + rows <= H; apron lanes / columns outside the image never flag
-            const unsigned nmine = __popc(fmask);
-            if (nmine) {
-                unsigned pos = atomicAdd(cnt, nmine);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (fmask & (1u << i)) buf[pos] = (addr_row + (unsigned)i) | (((cmask >> i) & 1u) << 31);
-                    pos += (fmask >> i) & 1u;
-                }
-            }
-            nstaged += __reduce_add_sync(0xffffffffu, nmine);
-            if (nstaged > (unsigned)(HW_FBUF - 128)) flush();
+            if (st_ok && n < y0 + rows) *bm_row = (uint8_t)((fmask & colmask) | (cmask << 4));   // n >= y0 >= 0, y0 + rows <= H
         }
-        addr_row += (unsigned)W;
+        bm_row += bm_pitch;
     };
     const int steps3 = (steps + 2) / 3 * 3;                  // the up to 2 extra steps read nothing and flag nothing
 #pragma unroll 1
@@ -486,16 +461,18 @@ __device__ __forceinline__ void harris_flag_strip(const uint8_t *__restrict__ or
         step(IntC<1>{}, j + 1);
         step(IntC<2>{}, j + 2);
     }
-    if (nstaged) flush();
 }
+
+// Flag bytes of image b: [H][bm_pitch] at the start of the image's key buffer (det.cand; the keys are written after
+// harris_compact_kernel has consumed the bytes).  Every (row, 4-column group) of the image is written by exactly one lane.
+__host__ __device__ __forceinline__ int harris_bm_pitch(int W) { return (((W + 3) >> 2) + 3) & ~3; }
 
 template <int MINB>
 __global__ void __launch_bounds__(HW_WARPS * 32, MINB)
 harris_flag_kernel(Pyramid pyr, SlotList slots, DetectScratch det, int tiles_x, int strips, int gl_narrow, int n_items, int hr_rows) {
-    __shared__ unsigned s_buf[HW_WARPS][HW_FBUF];
-    __shared__ unsigned s_cnt[HW_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
+    const int bm_pitch = harris_bm_pitch(W);
     const int total = n_items * slots.n;
     for (int wi = blockIdx.x * HW_WARPS + warp; wi < total; wi += gridDim.x * HW_WARPS) {
         const int b = wi / n_items, item = wi - b * n_items, slot = slots.v[b];
@@ -506,12 +483,50 @@ harris_flag_kernel(Pyramid pyr, SlotList slots, DetectScratch det, int tiles_x, 
             x0 = tiles_x * HR_COLS; y0 = (item - tiles_x * strips) * n_groups * hr_rows;
         }
         const uint8_t *org = pyr.image_origin(0, slot);
-        if (lane == 0) s_cnt[warp] = 0u;
-        __syncwarp();
+        uint8_t *bm = reinterpret_cast<uint8_t *>(det.cand + (size_t)b * det.cand_cap);
         // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+hr_rows+2 all inside the image
         const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
-        if (interior) harris_flag_strip<false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, det, b, s_buf[warp], &s_cnt[warp]);
-        else harris_flag_strip<true>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, det, b, s_buf[warp], &s_cnt[warp]);
+        if (interior) harris_flag_strip<false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, bm, bm_pitch);
+        else harris_flag_strip<true>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, bm, bm_pitch);
+    }
+}
+
+// Flag bytes -> list of flagged pixels (address | certain << 31) in the image's scratch buffer (det.cand2 viewed as
+// 32-bit entries: W * H of them, cannot overflow).  One 32-bit word = 16 pixels per thread.
+constexpr int HC_THREADS = 256;
+__global__ void __launch_bounds__(HC_THREADS)
+harris_compact_kernel(DetectScratch det, int W, int H) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int bm_pitch = harris_bm_pitch(W), wpr = bm_pitch >> 2, ngroups = (W + 3) >> 2;
+    const unsigned *bm = reinterpret_cast<const unsigned *>(det.cand + (size_t)b * det.cand_cap);
+    unsigned *list = reinterpret_cast<unsigned *>(det.cand2 + (size_t)b * det.cand_cap);
+    const int wi = blockIdx.x * HC_THREADS + threadIdx.x;
+    unsigned word = 0;
+    int row = 0, wcol = 0;
+    if (wi < wpr * H) {
+        row = wi / wpr; wcol = wi - row * wpr;
+        word = bm[wi];
+        const int valid = ngroups - 4 * wcol;              // bytes of this word that belong to the row (pad bytes are never written)
+        if (valid < 4) word &= valid <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - valid)));
+    }
+    unsigned f = word & 0x0F0F0F0Fu;
+    const unsigned mine = __popc(f);
+    unsigned inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+    if (tot == 0) return;                                   // warp-uniform
+    unsigned base = 0;
+    if (lane == 31) base = atomicAdd(&det.flag_count[b], tot);
+    unsigned pos = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
+    while (f) {
+        const int bit = __ffs(f) - 1;                       // 8 * byte + column within the group
+        f &= f - 1;
+        const unsigned x = (unsigned)(wcol * 16 + (bit >> 3) * 4 + (bit & 7));
+        list[pos++] = ((unsigned)row * (unsigned)W + x) | (((word >> (bit + 4)) & 1u) << 31);
     }
 }
 
@@ -535,7 +550,7 @@ harris_resolve_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det) {
         if (i < nflag) {
             const unsigned e = list[i], addr = e & 0x7FFFFFFFu;
             const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
-            const float v = harris_exact_at<kFma>(org, ipitch, W, H, x, y, k);
+            const float v = harris_exact<kFma>(org, ipitch, W, H, x, y, k);
             tmax = fmaxf(tmax, v);
             if (v > 0.0f && x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
                 bool ok = true;
@@ -607,7 +622,12 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
             RDFE_LAUNCH(ctx, K_HARRIS, (harris_flag_kernel<3><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
         else
             RDFE_LAUNCH(ctx, K_HARRIS, (harris_flag_kernel<4><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
-        // ~2.5 % of the pixels are flagged; a few CTAs per image walk the list
+        {
+            const int words = (harris_bm_pitch(g.w) >> 2) * g.h;
+            dim3 gc((words + HC_THREADS - 1) / HC_THREADS, slots.n);
+            RDFE_LAUNCH(ctx, K_HARRIS_COMPACT, (harris_compact_kernel<<<gc, HC_THREADS, 0, ctx->ls>>>(ctx->det, g.w, g.h)));
+        }
+        // ~5 % of the pixels are flagged; a few CTAs per image walk the list
         int gx = (kSMs * 8) / slots.n;
         gx = gx < 8 ? 8 : gx > 96 ? 96 : gx;
         dim3 g2(gx, slots.n);
@@ -615,7 +635,7 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
             RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<true><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det)));
         else
             RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<false><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det)));
-        return 3;
+        return 4;
     }
     if (p.harris_fma)
         RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));

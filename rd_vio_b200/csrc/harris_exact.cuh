@@ -73,6 +73,70 @@ __device__ __noinline__ float harris_exact_at(const uint8_t *__restrict__ org, i
     return (A * C - B * B) - k * ((A + C) * (A + C));
 }
 
+// float -> double for values that are zero or normal (gradient products are never subnormal unless zero: a non-zero
+// Sobel term is at least one ulp of an O(1e-4) float).  Integer re-biasing on the ALU pipe instead of the slow F2F.
+__device__ __forceinline__ double harris_f2d(float f) {
+    const unsigned u = __float_as_uint(f);
+    const unsigned mag = u & 0x7FFFFFFFu;
+    unsigned hi = (u & 0x80000000u) | ((mag >> 3) + 0x38000000u);
+    if (mag == 0u) hi = u;
+    return __hiloint2double((int)hi, (int)(u << 29));
+}
+
+// R(x, y) for 1 <= x <= W-2, 1 <= y <= H-2: every product position is inside the image (no reflection of the product
+// maps) and the 5x5 pixel patch lies inside the materialised halo.  Same arithmetic as harris_exact_at, with the row
+// terms of the 5 patch rows shared by the 9 positions (two aligned word loads per row).
+template <bool kFma>
+__device__ __forceinline__ float harris_exact_interior(const uint8_t *__restrict__ org, int ipitch, int x, int y, float k) {
+    const double sc = 1.0 / (4.0 * 3.0 * 255.0);
+    const float k0 = (float)sc, k1 = (float)(2.0 * sc);
+    const uint8_t *base = org + (ptrdiff_t)(y - 2) * ipitch + (x - 2);
+    const unsigned sh = ((unsigned)(size_t)base & 3u) * 8u;
+    const unsigned *wp = reinterpret_cast<const unsigned *>(base - (sh >> 3));
+    const int wpitch = ipitch >> 2;                          // row pitch is a multiple of 64 bytes
+    float d[5][3], s[5][3];                                  // [-1 0 1] and [k0 k1 k0] row terms at patch columns 1..3
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const unsigned w0 = wp[r * wpitch], w1 = wp[r * wpitch + 1];
+        const unsigned lo = __funnelshift_r(w0, w1, sh), hi = w1 >> sh;
+        float p[5];
+        p[0] = (float)(lo & 0xFFu); p[1] = (float)((lo >> 8) & 0xFFu); p[2] = (float)((lo >> 16) & 0xFFu);
+        p[3] = (float)(lo >> 24); p[4] = (float)(hi & 0xFFu);
+        float k0p[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) k0p[c] = k0 * p[c];
+#pragma unroll
+        for (int c = 1; c <= 3; ++c) {
+            d[r][c - 1] = p[c + 1] - p[c - 1];
+            if (!kFma) s[r][c - 1] = (k0p[c - 1] + k1 * p[c]) + k0p[c + 1];
+            else s[r][c - 1] = __fmaf_rn(k0, p[c + 1], __fmaf_rn(k1, p[c], k0p[c - 1]));
+        }
+    }
+    double a = 0.0, b = 0.0, c2 = 0.0;
+#pragma unroll
+    for (int r = 1; r <= 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float gx;
+            if (!kFma) gx = k1 * d[r][c] + k0 * (d[r - 1][c] + d[r + 1][c]);
+            else gx = __fmaf_rn(k0, d[r - 1][c] + d[r + 1][c], k1 * d[r][c]);
+            const float gy = s[r + 1][c] - s[r - 1][c];
+            a += harris_f2d(gx * gx);
+            b += harris_f2d(gx * gy);
+            c2 += harris_f2d(gy * gy);
+        }
+    const float A = (float)a, B = (float)b, C = (float)c2;
+    if (!kFma) return (A * C - B * B) - (k * (A + C)) * (A + C);
+    return (A * C - B * B) - k * ((A + C) * (A + C));
+}
+
+// dispatch: interior pixels take the patch path, the 1-px frame the general one
+template <bool kFma>
+__device__ __forceinline__ float harris_exact(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x, int y, float k) {
+    if (x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2) return harris_exact_interior<kFma>(org, ipitch, x, y, k);
+    return harris_exact_at<kFma>(org, ipitch, W, H, x, y, k);
+}
+
 // Whole-frame exact recomputation by ONE CTA (called by select_kernel for degenerate frames, see harris_exact.cuh):
 // response map into `map` (W*H floats), then the candidate keys and the frame maximum like the kernels above.
 __device__ __noinline__ static void harris_exact_all(const uint8_t *__restrict__ org, int ipitch, int W, int H, float k, bool fma, float *map,

@@ -15,5 +15,5 @@ except Exception as e: print("$f failed", e)
 PY
 done
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --profile-steps 0 > gpurun_out/r2_plain1.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.per_cycle_active -k regex:harris --clock-control none -c 12 --csv --log-file gpurun_out/r2_ncu_harris.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --profile-steps 0 > gpurun_out/r2_ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.per_cycle_active -k regex:harris --clock-control none -c 18 --csv --log-file gpurun_out/r2_ncu_harris.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --profile-steps 0 > gpurun_out/r2_ncu1.log 2>&1
 tail -15 gpurun_out/r2_ncu_harris.csv | cut -c1-300
