@@ -1139,7 +1139,7 @@ int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t b
 
 static const char *const kKernelNames[K_COUNT] = {"clahe_hist_lut", "clahe_apply", "pyrdown", "scharr",
                                                   "harris_nms", "select", "lk_track", "poisson_append", "undistort",
-                                                  "harris_resolve", "harris_compact"};
+                                                  "harris_resolve"};
 
 int rdfe_profile_num_kernels(void) { return K_COUNT; }
 const char *rdfe_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }

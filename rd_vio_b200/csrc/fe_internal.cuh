@@ -149,7 +149,7 @@ inline int adaptive_strip_rows(int height, int warps_per_row_strip, int min_rows
 }
 
 enum KernelId {
-    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_HARRIS_RESOLVE, K_HARRIS_COMPACT, K_COUNT
+    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_HARRIS_RESOLVE, K_COUNT
 };
 constexpr int kProfMax = 4096;      // timed launches between two rdfe_profile_collect calls
 
@@ -159,7 +159,7 @@ struct DetectScratch {
     unsigned *cand_count;         // [RDFE_MAX_BATCH]
     unsigned *frame_max;          // [RDFE_MAX_BATCH] max response bits (responses <= 0 never win)
     unsigned *overflow;           // [1]
-    unsigned *flag_count;         // [RDFE_MAX_BATCH] pixels flagged by the Harris prefilter (list: cand2 viewed as 32-bit entries)
+    unsigned *flag_count;         // [RDFE_MAX_BATCH] pixels flagged by the Harris prefilter (statistics; the flag bytes live in cand2)
     unsigned cand_cap;
 };
 

@@ -463,9 +463,8 @@ __device__ __forceinline__ void harris_flag_strip(const uint8_t *__restrict__ or
     }
 }
 
-// Flag bytes of image b: [H][bm_pitch] at the start of the image's key buffer (det.cand; the keys are written after
-// harris_compact_kernel has consumed the bytes).  Every (row, 4-column group) of the image is written by exactly one lane.
-__host__ __device__ __forceinline__ int harris_bm_pitch(int W) { return (((W + 3) >> 2) + 3) & ~3; }
+// Flag bytes of image b: [H][bm_pitch] at the start of the image's scratch buffer (det.cand2, free between two selections).  Every (row, 4-column group) of the image is written by exactly one lane.
+__host__ __device__ __forceinline__ int harris_bm_pitch(int W) { return (((W + 3) >> 2) + 7) & ~7; }
 
 template <int MINB>
 __global__ void __launch_bounds__(HW_WARPS * 32, MINB)
@@ -483,7 +482,7 @@ harris_flag_kernel(Pyramid pyr, SlotList slots, DetectScratch det, int tiles_x, 
             x0 = tiles_x * HR_COLS; y0 = (item - tiles_x * strips) * n_groups * hr_rows;
         }
         const uint8_t *org = pyr.image_origin(0, slot);
-        uint8_t *bm = reinterpret_cast<uint8_t *>(det.cand + (size_t)b * det.cand_cap);
+        uint8_t *bm = reinterpret_cast<uint8_t *>(det.cand2 + (size_t)b * det.cand_cap);
         // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+hr_rows+2 all inside the image
         const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
         if (interior) harris_flag_strip<false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, bm, bm_pitch);
@@ -491,80 +490,39 @@ harris_flag_kernel(Pyramid pyr, SlotList slots, DetectScratch det, int tiles_x, 
     }
 }
 
-// Flag bytes -> list of flagged pixels (address | certain << 31) in the image's scratch buffer (det.cand2 viewed as
-// 32-bit entries: W * H of them, cannot overflow).  One 32-bit word = 16 pixels per thread.
-constexpr int HC_THREADS = 256;
-__global__ void __launch_bounds__(HC_THREADS)
-harris_compact_kernel(DetectScratch det, int W, int H) {
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int bm_pitch = harris_bm_pitch(W), wpr = bm_pitch >> 2, ngroups = (W + 3) >> 2;
-    const unsigned *bm = reinterpret_cast<const unsigned *>(det.cand + (size_t)b * det.cand_cap);
-    unsigned *list = reinterpret_cast<unsigned *>(det.cand2 + (size_t)b * det.cand_cap);
-    const int wi = blockIdx.x * HC_THREADS + threadIdx.x;
-    unsigned word = 0;
-    int row = 0, wcol = 0;
-    if (wi < wpr * H) {
-        row = wi / wpr; wcol = wi - row * wpr;
-        word = bm[wi];
-        const int valid = ngroups - 4 * wcol;              // bytes of this word that belong to the row (pad bytes are never written)
-        if (valid < 4) word &= valid <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - valid)));
-    }
-    unsigned f = word & 0x0F0F0F0Fu;
-    const unsigned mine = __popc(f);
-    unsigned inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
-    if (tot == 0) return;                                   // warp-uniform
-    unsigned base = 0;
-    if (lane == 31) base = atomicAdd(&det.flag_count[b], tot);
-    unsigned pos = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
-    while (f) {
-        const int bit = __ffs(f) - 1;                       // 8 * byte + column within the group
-        f &= f - 1;
-        const unsigned x = (unsigned)(wcol * 16 + (bit >> 3) * 4 + (bit & 7));
-        list[pos++] = ((unsigned)row * (unsigned)W + x) | (((word >> (bit + 4)) & 1u) << 31);
-    }
-}
-
-// Exact response at the flagged pixels: 64-bit keys of the positive 3x3 local maxima off the 1-px frame (the
-// candidates of goodFeaturesToTrack before its threshold) and the frame maximum.
+// Exact response at the flagged pixels: 64-bit keys of the positive 3x3 local maxima off the 1-px frame (the candidates
+// of goodFeaturesToTrack before its threshold) and the frame maximum.
+//   * a warp reads 32 x 8 flag bytes (1024 pixels), compacts the flagged pixels into its shared-memory buffer with a
+//     shuffle scan and evaluates them 32 at a time, so that every lane always has a pixel (the remainder is carried to
+//     the next chunk);
+//   * pixels that are not CERTAIN maxima need their 8 neighbours' exact responses: they go to a CTA-wide queue that
+//     is worked off at the end with one (pixel, neighbour) pair per thread -- handled in place they would make whole
+//     warps wait for a lane that evaluates nine pixels.
 constexpr int HV_THREADS = 256;
+constexpr int HV_WBUF = 1024 + 32;     // per-warp buffer: one chunk (every pixel flagged) + a carried remainder
+constexpr int HV_QCAP = 1024;          // uncertain pixels per CTA before the in-place fallback
 template <bool kFma>
 __global__ void __launch_bounds__(HV_THREADS)
-harris_resolve_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det) {
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
+harris_resolve_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, int chunks_per_warp) {
+    __shared__ unsigned s_buf[HV_THREADS / 32][HV_WBUF];
+    __shared__ unsigned q_addr[HV_QCAP];
+    __shared__ float q_val[HV_QCAP];
+    __shared__ unsigned q_ok[HV_QCAP];
+    __shared__ unsigned q_n;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
     const uint8_t *org = pyr.image_origin(0, slots.v[b]);
-    const unsigned nflag = det.flag_count[b];
-    const unsigned *list = reinterpret_cast<const unsigned *>(det.cand2 + (size_t)b * det.cand_cap);
+    const int bm_pitch = harris_bm_pitch(W), ngroups = (W + 3) >> 2;
+    const unsigned long long *bm = det.cand2 + (size_t)b * det.cand_cap;       // flag bytes, read as 8-byte words
     unsigned long long *out = det.cand + (size_t)b * det.cand_cap;
+    const int nwords = (bm_pitch >> 3) * H, wpr = bm_pitch >> 3;
+    if (threadIdx.x == 0) q_n = 0u;
+    __syncthreads();
+    unsigned *buf = s_buf[warp];
     float tmax = 0.0f;
-    for (unsigned base = blockIdx.x * HV_THREADS; base < nflag; base += gridDim.x * HV_THREADS) {   // CTA-uniform
-        const unsigned i = base + threadIdx.x;
-        bool emit = false;
-        unsigned long long key = 0ull;
-        if (i < nflag) {
-            const unsigned e = list[i], addr = e & 0x7FFFFFFFu;
-            const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
-            const float v = harris_exact<kFma>(org, ipitch, W, H, x, y, k);
-            tmax = fmaxf(tmax, v);
-            if (v > 0.0f && x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
-                bool ok = true;
-                if (!(e >> 31)) {                            // not certain: compare with the exact neighbours
-#pragma unroll 1
-                    for (int t = 0; t < 9; ++t) {
-                        if (t == 4) continue;
-                        if (v < harris_exact_at<kFma>(org, ipitch, W, H, x + t % 3 - 1, y + t / 3 - 1, k)) ok = false;
-                    }
-                }
-                emit = ok;
-                key = ((unsigned long long)__float_as_uint(v) << 32) | addr;
-            }
-        }
+    unsigned nbuf = 0, nflag = 0;                            // warp-uniform
+
+    auto emit_keys = [&](bool emit, unsigned long long key) {   // warp-aggregated append (all lanes call)
         const unsigned m = __ballot_sync(0xffffffffu, emit);
         if (m) {
             unsigned pos = 0;
@@ -575,7 +533,88 @@ harris_resolve_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det) {
                 else atomicExch(det.overflow, 1u);
             }
         }
+    };
+    auto eval32 = [&](unsigned e, bool have) {                // one flagged pixel per lane
+        bool emit = false;
+        unsigned long long key = 0ull;
+        if (have) {
+            const unsigned addr = e & 0x7FFFFFFFu;
+            const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
+            const float v = harris_exact<kFma>(org, ipitch, W, H, x, y, k);
+            tmax = fmaxf(tmax, v);
+            if (v > 0.0f && x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+                key = ((unsigned long long)__float_as_uint(v) << 32) | addr;
+                if (e >> 31) emit = true;
+                else {
+                    const unsigned qp = atomicAdd(&q_n, 1u);
+                    if (qp < HV_QCAP) { q_addr[qp] = addr; q_val[qp] = v; q_ok[qp] = 1u; }
+                    else {                                   // queue full (pathological frames): in place
+                        emit = true;
+#pragma unroll 1
+                        for (int t = 0; t < 9; ++t)
+                            if (t != 4 && v < harris_exact_at<kFma>(org, ipitch, W, H, x + t % 3 - 1, y + t / 3 - 1, k)) emit = false;
+                    }
+                }
+            }
+        }
+        emit_keys(emit, key);
+    };
+
+    const int warp_id = (blockIdx.x * (HV_THREADS / 32) + warp);
+    const int first = warp_id * chunks_per_warp * 32;        // first 8-byte word of this warp
+    for (int c = 0; c < chunks_per_warp; ++c) {
+        const int wi = first + c * 32 + lane;
+        if (first + c * 32 >= nwords) break;                 // warp-uniform
+        unsigned long long word = 0ull;
+        int row = 0, cb = 0;
+        if (wi < nwords) {
+            row = wi / wpr; cb = (wi - row * wpr) * 8;       // first group (= byte) of this word within the row
+            word = bm[wi];
+            const int valid = ngroups - cb;                  // bytes that belong to the row (pad bytes are never written)
+            if (valid < 8) word &= valid <= 0 ? 0ull : (~0ull >> (8 * (8 - valid)));
+        }
+        unsigned long long f = word & 0x0F0F0F0F0F0F0F0Full;
+        const unsigned mine = __popcll(f);
+        unsigned inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+        unsigned pos = nbuf + inc - mine;
+        const unsigned rowaddr = (unsigned)row * (unsigned)W + (unsigned)cb * 4u;
+        while (f) {
+            const int bit = __ffsll((long long)f) - 1;       // 8 * byte + column within the group
+            f &= f - 1;
+            buf[pos++] = (rowaddr + (unsigned)((bit >> 3) * 4 + (bit & 7))) | ((unsigned)((word >> (bit + 4)) & 1ull) << 31);
+        }
+        nbuf += tot; nflag += tot;
+        __syncwarp();
+        while (nbuf >= 32u) {                                // full groups only: every lane has a pixel
+            nbuf -= 32u;
+            eval32(buf[nbuf + lane], true);
+        }
+        __syncwarp();
     }
+    if (nbuf) eval32(lane < nbuf ? buf[lane] : 0u, lane < nbuf);
+    if (lane == 0 && nflag) atomicAdd(&det.flag_count[b], nflag);
+    __syncthreads();
+    // ---- uncertain pixels: one (pixel, neighbour) pair per thread
+    const unsigned nq = min(q_n, (unsigned)HV_QCAP);
+    for (unsigned t = threadIdx.x; t < nq * 8u; t += HV_THREADS) {
+        const unsigned e = t >> 3, nb = (t & 7u) < 4u ? (t & 7u) : (t & 7u) + 1u;
+        const unsigned addr = q_addr[e];
+        const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
+        if (q_val[e] < harris_exact<kFma>(org, ipitch, W, H, x + (int)(nb % 3u) - 1, y + (int)(nb / 3u) - 1, k)) q_ok[e] = 0u;
+    }
+    __syncthreads();
+    for (unsigned e = threadIdx.x; e < nq; e += HV_THREADS)
+        if (q_ok[e]) {
+            const unsigned pos = atomicAdd(&det.cand_count[b], 1u);
+            if (pos < det.cand_cap) out[pos] = ((unsigned long long)__float_as_uint(q_val[e]) << 32) | q_addr[e];
+            else atomicExch(det.overflow, 1u);
+        }
     const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
     if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
 }
@@ -590,7 +629,6 @@ static bool harris_narrow_enabled() {
     static const bool v = [] { const char *e = getenv("RDFE_HARRIS_NARROW"); return !(e && e[0] == '0'); }();
     return v;
 }
-
 static bool harris_prefilter_enabled() {
     static const bool v = [] { const char *e = getenv("RDFE_HARRIS_EXACT"); return !(e && e[0] == '1'); }();
     return v;
@@ -622,20 +660,17 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
             RDFE_LAUNCH(ctx, K_HARRIS, (harris_flag_kernel<3><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
         else
             RDFE_LAUNCH(ctx, K_HARRIS, (harris_flag_kernel<4><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
-        {
-            const int words = (harris_bm_pitch(g.w) >> 2) * g.h;
-            dim3 gc((words + HC_THREADS - 1) / HC_THREADS, slots.n);
-            RDFE_LAUNCH(ctx, K_HARRIS_COMPACT, (harris_compact_kernel<<<gc, HC_THREADS, 0, ctx->ls>>>(ctx->det, g.w, g.h)));
-        }
-        // ~5 % of the pixels are flagged; a few CTAs per image walk the list
-        int gx = (kSMs * 8) / slots.n;
-        gx = gx < 8 ? 8 : gx > 96 ? 96 : gx;
-        dim3 g2(gx, slots.n);
+        // a warp of the resolve kernel takes `cpw` chunks of 1024 pixels; enough warps to fill the GPU at small batches
+        const int nwords = (harris_bm_pitch(g.w) >> 3) * g.h, nchunks = (nwords + 31) / 32;
+        int cpw = (nchunks * slots.n + kSMs * 16 - 1) / (kSMs * 16);
+        cpw = cpw < 1 ? 1 : cpw > 4 ? 4 : cpw;
+        const int warps = (nchunks + cpw - 1) / cpw;
+        dim3 g2((warps + HV_THREADS / 32 - 1) / (HV_THREADS / 32), slots.n);
         if (p.harris_fma)
-            RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<true><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det)));
+            RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<true><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, cpw)));
         else
-            RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<false><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det)));
-        return 4;
+            RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<false><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, cpw)));
+        return 3;
     }
     if (p.harris_fma)
         RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
