@@ -619,6 +619,262 @@ harris_resolve_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, i
     if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// harris_strip3: same arithmetic as harris_strip (every float op of the reference, individually rounded), re-mapped for
+// Blackwell's issue limits:
+//   * the float32 stages work on PAIRS of pixels with FADD2 / FMUL2 / FFMA2 (pixels 0 and 2 of the lane in one
+//     register pair, 1 and 3 in another, so that the left / centre / right taps of a pair are again pairs);
+//   * all row histories (Sobel row terms, products, responses) live in rings of three registers indexed at compile
+//     time, the loop body is unrolled three times: no register is ever moved;
+//   * 3-input FMNMX3 for the 3x3 maxima, box sums with shared pair sums (6 instead of 8 DADD per quantity).
+// The float64 box sums are exact, so their order is free; every float32 operation is the same IEEE operation on the
+// same operands as before -- the packed instructions round each half independently.
+__device__ __forceinline__ F2 f2_sub(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 f2_set(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ F2 f2_xor(F2 a, unsigned long long m) { F2 r; r.v = a.v ^ m; return r; }
+
+template <bool kFma, bool BORDER>
+__device__ __forceinline__ void harris_strip3(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0w, int hr_rows, int gl_lanes,
+                                              int n_groups, float k, const DetectScratch &det, int b, unsigned long long *buf, unsigned *cnt) {
+    const int lane = threadIdx.x & 31;
+    const int GL = BORDER ? gl_lanes : 32;
+    const int grp = BORDER ? lane / GL : 0;
+    const int gl = lane - grp * GL;
+    const int y0 = y0w + grp * hr_rows;
+    const bool active = !BORDER || (grp < n_groups && y0 < H);
+    const int c0 = x0 - 4 + 4 * gl;
+    const bool ld_ok = BORDER ? (active && (c0 + 3 <= W + 20) && (c0 >= -20)) : true;
+    const bool out_lane = active && gl >= 1 && gl <= GL - 2;
+    const double sc = 1.0 / (4.0 * 3.0 * 255.0);
+    const float k0 = (float)sc, k1 = (float)(2.0 * sc);
+    const F2 K0 = f2_set(k0), K1 = f2_set(k1), KK = f2_set(k);
+    // per-column flags (BORDER only).  Pair E = columns (c0, c0+2), pair O = (c0+1, c0+3).
+    int mir_col = -1;                                        // lane-local index of a mirrored column (x == -1 or x == W), if any
+    unsigned long long flipE[2] = {0ull, 0ull}, flipO[2] = {0ull, 0ull};   // sign masks of gx*gy for rows inside / outside the image
+    float cinv[4], cemit[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = c0 + i;
+        const bool outside = BORDER && (x < 0 || x >= W);
+        if (BORDER && (x == -1 || x == W)) mir_col = i;
+        const unsigned long long bit = 0x80000000ull << ((i >> 1) * 32);
+        if (outside) { if (i & 1) flipO[0] |= bit; else flipE[0] |= bit; }   // row inside: flip where the column is mirrored
+        else if (BORDER) { if (i & 1) flipO[1] |= bit; else flipE[1] |= bit; }   // row outside: flip where the column is not
+        cinv[i] = outside ? -INFINITY : 0.0f;
+        cemit[i] = (!out_lane || (BORDER && (x < 1 || x >= W - 1))) ? -INFINITY : 0.0f;
+    }
+    const F2 cinvE = f2_pack(cinv[0], cinv[2]), cinvO = f2_pack(cinv[1], cinv[3]);
+
+    // rings (slot = step % 3): Sobel row terms d, s (pairs E, O); products as doubles; responses
+    F2 dE[3], dO[3], sE[3], sO[3];
+    double qa[3][4], qb[3][4], qc[3][4];
+    float Rr[3][6], Rx[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        dE[r] = dO[r] = sE[r] = sO[r] = f2_set(0.0f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qa[r][i] = 0.0; qb[r][i] = 0.0; qc[r][i] = 0.0; Rx[r][i] = -INFINITY; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Rr[r][i] = -INFINITY;
+    }
+    float tmax = 0.0f;
+
+    unsigned nstaged = 0;
+    auto flush = [&]() {
+        const unsigned nb = nstaged;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&det.cand_count[b], nb);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (unsigned i = lane; i < nb; i += 32) {
+            const unsigned pos = base + i;
+            if (pos < det.cand_cap) det.cand[(size_t)b * det.cand_cap + pos] = buf[i];
+            else atomicExch(det.overflow, 1u);
+        }
+        __syncwarp();
+        if (lane == 0) *cnt = 0u;
+        nstaged = 0;
+        __syncwarp();
+    };
+
+    const int rows = active ? min(hr_rows, H - y0) : 0;
+    const int steps = min(hr_rows, H - y0w) + 6;
+    const int my_steps = BORDER ? rows + 6 : steps;
+    const uint8_t *rowp = org + (ptrdiff_t)(y0 - 3) * ipitch + c0;
+    unsigned wq0 = 0, wq1 = 0;
+    if (ld_ok) { wq0 = *reinterpret_cast<const unsigned *>(rowp); wq1 = *reinterpret_cast<const unsigned *>(rowp + ipitch); }
+    rowp += 2 * (ptrdiff_t)ipitch;
+    unsigned addr_row = (unsigned)((y0 - 6) * W + c0);
+
+    auto step = [&](auto ph, int j) {
+        constexpr int R0 = decltype(ph)::value, R1 = (R0 + 1) % 3, R2 = (R0 + 2) % 3;   // R0: this row; R1: two rows up; R2: one row up
+        const unsigned w = wq0;
+        wq0 = wq1;
+        if (ld_ok && j + 2 < my_steps) wq1 = *reinterpret_cast<const unsigned *>(rowp);
+        rowp += ipitch;
+        const unsigned wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+        // pixel pairs as floats: Pa = (p[-1], p[1]), Pb = (p[0], p[2]), Pc = (p[1], p[3]), Pd = (p[2], p[4]) relative to c0
+        const F2 M23 = f2_set(-8388608.0f);
+        const F2 Pa = f2_add(f2_pack(__uint_as_float(__byte_perm(wl, 0x4B000000u, 0x7653u)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651u))), M23);
+        const F2 Pb = f2_add(f2_pack(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652u))), M23);
+        const F2 Pc = f2_add(f2_pack(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651u)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653u))), M23);
+        const F2 Pd = f2_add(f2_pack(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652u)), __uint_as_float(__byte_perm(wr, 0x4B000000u, 0x7650u))), M23);
+        // ---- Sobel row terms of this row (ring slot R0): pair E has taps (Pa, Pb, Pc), pair O has (Pb, Pc, Pd)
+        dE[R0] = f2_sub(Pc, Pa);
+        dO[R0] = f2_sub(Pd, Pb);
+        const F2 k0a = f2_mul(K0, Pa), k0b = f2_mul(K0, Pb), k0c = f2_mul(K0, Pc), k0d = f2_mul(K0, Pd);
+        if (!kFma) {
+            sE[R0] = f2_add(f2_add(k0a, f2_mul(K1, Pb)), k0c);
+            sO[R0] = f2_add(f2_add(k0b, f2_mul(K1, Pc)), k0d);
+        } else {
+            sE[R0] = f2_fma(K0, Pc, f2_fma(K1, Pb, k0a));
+            sO[R0] = f2_fma(K0, Pd, f2_fma(K1, Pc, k0b));
+        }
+        if (BORDER && mir_col >= 0) {
+            // the column x == -1 / x == W: the 3-tap smoothing in mirrored order (it is not associative)
+            float pl, pc, pr2, e0, e1;
+            const bool odd = mir_col & 1, hi = mir_col >> 1;
+            f2_unpack(odd ? Pb : Pa, e0, e1); pl = hi ? e1 : e0;
+            f2_unpack(odd ? Pc : Pb, e0, e1); pc = hi ? e1 : e0;
+            f2_unpack(odd ? Pd : Pc, e0, e1); pr2 = hi ? e1 : e0;
+            float sv;
+            if (!kFma) sv = ((k0 * pr2) + k1 * pc) + k0 * pl;
+            else sv = __fmaf_rn(k0, pl, __fmaf_rn(k1, pc, k0 * pr2));
+            F2 &dst = odd ? sO[R0] : sE[R0];
+            f2_unpack(dst, e0, e1);
+            dst = hi ? f2_pack(e0, sv) : f2_pack(sv, e1);
+        }
+        // ---- gradients of the row above (centre R2: rows R1, R2, R0), products, exact box sums
+        const int pr = y0 - 4 + j;
+        const bool bflipy = BORDER && ((pr < 0) || (pr >= H));
+        F2 gxE, gxO;
+        if (!kFma) {
+            gxE = f2_add(f2_mul(K1, dE[R2]), f2_mul(K0, f2_add(dE[R1], dE[R0])));
+            gxO = f2_add(f2_mul(K1, dO[R2]), f2_mul(K0, f2_add(dO[R1], dO[R0])));
+        } else {
+            gxE = f2_fma(K0, f2_add(dE[R1], dE[R0]), f2_mul(K1, dE[R2]));
+            gxO = f2_fma(K0, f2_add(dO[R1], dO[R0]), f2_mul(K1, dO[R2]));
+        }
+        const F2 gyE = f2_sub(sE[R0], sE[R1]), gyO = f2_sub(sO[R0], sO[R1]);
+        F2 fbE = f2_mul(gxE, gyE), fbO = f2_mul(gxO, gyO);
+        if (BORDER) { fbE = f2_xor(fbE, flipE[bflipy ? 1 : 0]); fbO = f2_xor(fbO, flipO[bflipy ? 1 : 0]); }
+        const F2 faE = f2_mul(gxE, gxE), faO = f2_mul(gxO, gxO), fcE = f2_mul(gyE, gyE), fcO = f2_mul(gyO, gyO);
+        {
+            float e0, e1;
+            f2_unpack(faE, e0, e1); qa[R0][0] = (double)e0; qa[R0][2] = (double)e1;
+            f2_unpack(faO, e0, e1); qa[R0][1] = (double)e0; qa[R0][3] = (double)e1;
+            f2_unpack(fbE, e0, e1); qb[R0][0] = (double)e0; qb[R0][2] = (double)e1;
+            f2_unpack(fbO, e0, e1); qb[R0][1] = (double)e0; qb[R0][3] = (double)e1;
+            f2_unpack(fcE, e0, e1); qc[R0][0] = (double)e0; qc[R0][2] = (double)e1;
+            f2_unpack(fcO, e0, e1); qc[R0][1] = (double)e0; qc[R0][3] = (double)e1;
+        }
+        double va[6], vb[6], vc[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            va[i + 1] = (qa[R1][i] + qa[R2][i]) + qa[R0][i];
+            vb[i + 1] = (qb[R1][i] + qb[R2][i]) + qb[R0][i];
+            vc[i + 1] = (qc[R1][i] + qc[R2][i]) + qc[R0][i];
+        }
+        va[0] = shfl_up_d(va[4]); vb[0] = shfl_up_d(vb[4]); vc[0] = shfl_up_d(vc[4]);
+        va[5] = shfl_down_d(va[1]); vb[5] = shfl_down_d(vb[1]); vc[5] = shfl_down_d(vc[1]);
+        float A[4], B[4], C[4];
+        {
+            const double a12 = va[1] + va[2], a34 = va[3] + va[4], b12 = vb[1] + vb[2], b34 = vb[3] + vb[4];
+            const double c12 = vc[1] + vc[2], c34 = vc[3] + vc[4];
+            A[0] = (float)(va[0] + a12); A[1] = (float)(a12 + va[3]); A[2] = (float)(va[2] + a34); A[3] = (float)(a34 + va[5]);
+            B[0] = (float)(vb[0] + b12); B[1] = (float)(b12 + vb[3]); B[2] = (float)(vb[2] + b34); B[3] = (float)(b34 + vb[5]);
+            C[0] = (float)(vc[0] + c12); C[1] = (float)(c12 + vc[3]); C[2] = (float)(vc[2] + c34); C[3] = (float)(c34 + vc[5]);
+        }
+        // ---- response of row q = pr - 1 (ring slot R0 of the response rings)
+        const int q = pr - 1;
+        {
+            const F2 A01 = f2_pack(A[0], A[1]), A23 = f2_pack(A[2], A[3]), B01 = f2_pack(B[0], B[1]), B23 = f2_pack(B[2], B[3]);
+            const F2 C01 = f2_pack(C[0], C[1]), C23 = f2_pack(C[2], C[3]);
+            const F2 T01 = f2_add(A01, C01), T23 = f2_add(A23, C23);
+            const F2 D01 = f2_sub(f2_mul(A01, C01), f2_mul(B01, B01)), D23 = f2_sub(f2_mul(A23, C23), f2_mul(B23, B23));
+            F2 r01, r23;
+            if (!kFma) { r01 = f2_sub(D01, f2_mul(f2_mul(KK, T01), T01)); r23 = f2_sub(D23, f2_mul(f2_mul(KK, T23), T23)); }
+            else { r01 = f2_sub(D01, f2_mul(KK, f2_mul(T01, T01))); r23 = f2_sub(D23, f2_mul(KK, f2_mul(T23, T23))); }
+            if (BORDER) {
+                // dilate ignores pixels outside the image: -inf there (v + 0 is exact, v - inf = -inf)
+                const float rinv = (q < 0 || q >= H) ? -INFINITY : 0.0f;
+                r01 = f2_add(r01, f2_pack(cinv[0] + rinv, cinv[1] + rinv));
+                r23 = f2_add(r23, f2_pack(cinv[2] + rinv, cinv[3] + rinv));
+            }
+            f2_unpack(r01, Rr[R0][1], Rr[R0][2]);
+            f2_unpack(r23, Rr[R0][3], Rr[R0][4]);
+        }
+        Rr[R0][0] = __shfl_up_sync(0xffffffffu, Rr[R0][4], 1);
+        Rr[R0][5] = __shfl_down_sync(0xffffffffu, Rr[R0][1], 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Rx[R0][i] = fmax3(Rr[R0][i], Rr[R0][i + 1], Rr[R0][i + 2]);
+        // ---- NMS for row n = q-1 (raw row in slot R2): rows n-1 (slot R1, max3), n, n+1 (slot R0, max3)
+        const int n = q - 1;
+        if (j >= 6) {
+            const bool nrow_ok = (n < y0 + rows) && (!BORDER || ((n >= 1) && (n < H - 1)));
+            unsigned cmask = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = Rr[R2][i + 1];
+                const float m = fmax3(Rx[R1][i], Rx[R0][i], fmaxf(Rr[R2][i], Rr[R2][i + 2]));
+                const float ve = v + cemit[i];               // -inf where this lane/column may not emit
+                if (ve > 0.0f && ve >= m) cmask |= 1u << i;
+            }
+            // frame maximum over every row of the strip (the rounded-up trip count must not leak rows computed from stale
+            // pixels); -inf outside the image never wins
+            if (out_lane && n < y0 + rows) { tmax = fmax3(tmax, Rr[R2][1], Rr[R2][2]); tmax = fmax3(tmax, Rr[R2][3], Rr[R2][4]); }
+            if (!nrow_ok) cmask = 0;
+            const unsigned nmine = __popc(cmask);
+            if (nmine) {
+                unsigned pos = atomicAdd(cnt, nmine);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (cmask & (1u << i)) buf[pos] = ((unsigned long long)__float_as_uint(Rr[R2][i + 1]) << 32) | (addr_row + (unsigned)i);
+                    pos += (cmask >> i) & 1u;
+                }
+            }
+            nstaged += __reduce_add_sync(0xffffffffu, nmine);
+            if (nstaged > (unsigned)(HW_BUF - 128)) flush();    // warp-uniform: a step adds at most 120 keys
+        }
+        addr_row += (unsigned)W;
+    };
+    const int steps3 = (steps + 2) / 3 * 3;                  // the up to 2 extra steps read nothing and emit nothing
+#pragma unroll 1
+    for (int j = 0; j < steps3; j += 3) {
+        step(IntC<0>{}, j);
+        step(IntC<1>{}, j + 1);
+        step(IntC<2>{}, j + 2);
+    }
+    if (nstaged) flush();
+    const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
+    if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
+}
+
+template <bool kFma>
+__global__ void __launch_bounds__(HW_WARPS * 32)
+harris_nms3_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, int tiles_x, int strips, int gl_narrow, int n_items, int hr_rows) {
+    __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
+    __shared__ unsigned s_cnt[HW_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = pyr.lv[0].w, H = pyr.lv[0].h, ipitch = pyr.lv[0].ipitch;
+    const int total = n_items * slots.n;
+    for (int wi = blockIdx.x * HW_WARPS + warp; wi < total; wi += gridDim.x * HW_WARPS) {
+        const int b = wi / n_items, item = wi - b * n_items, slot = slots.v[b];
+        int x0, y0, gl_lanes = 32, n_groups = 1;
+        if (item < tiles_x * strips) { x0 = (item % tiles_x) * HR_COLS; y0 = (item / tiles_x) * hr_rows; }
+        else {
+            gl_lanes = gl_narrow; n_groups = gl_narrow == 10 ? 3 : 2;
+            x0 = tiles_x * HR_COLS; y0 = (item - tiles_x * strips) * n_groups * hr_rows;
+        }
+        const uint8_t *org = pyr.image_origin(0, slot);
+        if (lane == 0) s_cnt[warp] = 0u;
+        __syncwarp();
+        const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
+        if (interior) harris_strip3<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, k, det, b, s_buf[warp], &s_cnt[warp]);
+        else harris_strip3<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, k, det, b, s_buf[warp], &s_cnt[warp]);
+    }
+}
+
 // Experiment switches (environment, read once): RDFE_HARRIS_ROWS = strip height at full batches, RDFE_HARRIS_NARROW=0
 // walks the narrow last tile one strip per warp like the full tiles.
 static int harris_max_rows() {
@@ -629,8 +885,11 @@ static bool harris_narrow_enabled() {
     static const bool v = [] { const char *e = getenv("RDFE_HARRIS_NARROW"); return !(e && e[0] == '0'); }();
     return v;
 }
-static bool harris_prefilter_enabled() {
-    static const bool v = [] { const char *e = getenv("RDFE_HARRIS_EXACT"); return !(e && e[0] == '1'); }();
+// RDFE_HARRIS_IMPL: 3 (default) = packed exact kernel harris_nms3_kernel; 0 = the round-1 exact kernel harris_nms_kernel;
+// 1 = integer prefilter + exact evaluation of the flagged pixels (harris_flag_kernel / harris_resolve_kernel).  All three
+// emit identical keys (tests/test_gpu_harris_prefilter.py runs each).
+static int harris_impl() {
+    static const int v = [] { const char *e = getenv("RDFE_HARRIS_IMPL"); const int r = e ? atoi(e) : 3; return (r == 0 || r == 1) ? r : 3; }();
     return v;
 }
 
@@ -653,7 +912,7 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
     const int n_items = tiles_x * strips + (gl_narrow ? (strips + n_groups - 1) / n_groups : 0);
     const int total = n_items * slots.n;
     dim3 grid((total + HW_WARPS - 1) / HW_WARPS);     // one warp per (image, strip); the kernel's loop also accepts fewer
-    if (!d_response && harris_prefilter_enabled()) {
+    if (!d_response && harris_impl() == 1) {
         // RDFE_HARRIS_MB=3: 153 registers, no spills, 12 warps per SM; 4 (default): 128 registers, 16 warps per SM
         static const int minb = [] { const char *e = getenv("RDFE_HARRIS_MB"); return e ? atoi(e) : 4; }();
         if (minb == 3)
@@ -671,6 +930,13 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
         else
             RDFE_LAUNCH(ctx, K_HARRIS_RESOLVE, (harris_resolve_kernel<false><<<g2, HV_THREADS, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, cpw)));
         return 3;
+    }
+    if (!d_response && harris_impl() == 3) {
+        if (p.harris_fma)
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms3_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        else
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms3_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        return 2;
     }
     if (p.harris_fma)
         RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));

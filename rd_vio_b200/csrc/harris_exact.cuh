@@ -74,13 +74,18 @@ __device__ __noinline__ float harris_exact_at(const uint8_t *__restrict__ org, i
 }
 
 // float -> double for values that are zero or normal (gradient products are never subnormal unless zero: a non-zero
-// Sobel term is at least one ulp of an O(1e-4) float).  Integer re-biasing on the ALU pipe instead of the slow F2F.
+// Sobel term is at least one ulp of an O(1e-4) float).  Integer re-biasing on the ALU pipe instead of the slow F2F:
+// exponent + 896 unless the value is zero (min(mag >> 3, 1) is 0 only for zero).
 __device__ __forceinline__ double harris_f2d(float f) {
     const unsigned u = __float_as_uint(f);
-    const unsigned mag = u & 0x7FFFFFFFu;
-    unsigned hi = (u & 0x80000000u) | ((mag >> 3) + 0x38000000u);
-    if (mag == 0u) hi = u;
+    const unsigned t = (u & 0x7FFFFFFFu) >> 3;
+    const unsigned hi = (u & 0x80000000u) | (t + min(t, 1u) * 0x38000000u);
     return __hiloint2double((int)hi, (int)(u << 29));
+}
+__device__ __forceinline__ double harris_f2d_nonneg(float f) {      // f >= +0
+    const unsigned u = __float_as_uint(f);
+    const unsigned t = u >> 3;
+    return __hiloint2double((int)(t + min(t, 1u) * 0x38000000u), (int)(u << 29));
 }
 
 // R(x, y) for 1 <= x <= W-2, 1 <= y <= H-2: every product position is inside the image (no reflection of the product
@@ -98,10 +103,14 @@ __device__ __forceinline__ float harris_exact_interior(const uint8_t *__restrict
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         const unsigned w0 = wp[r * wpitch], w1 = wp[r * wpitch + 1];
-        const unsigned lo = __funnelshift_r(w0, w1, sh), hi = w1 >> sh;
+        const unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, 0u, sh);
+        // byte -> float: PRMT builds the bits of 2^23 + b, one FADD removes the 2^23 (exact)
         float p[5];
-        p[0] = (float)(lo & 0xFFu); p[1] = (float)((lo >> 8) & 0xFFu); p[2] = (float)((lo >> 16) & 0xFFu);
-        p[3] = (float)(lo >> 24); p[4] = (float)(hi & 0xFFu);
+        p[0] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7650u)) - 8388608.0f;
+        p[1] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7651u)) - 8388608.0f;
+        p[2] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7652u)) - 8388608.0f;
+        p[3] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7653u)) - 8388608.0f;
+        p[4] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7650u)) - 8388608.0f;
         float k0p[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) k0p[c] = k0 * p[c];
@@ -121,9 +130,9 @@ __device__ __forceinline__ float harris_exact_interior(const uint8_t *__restrict
             if (!kFma) gx = k1 * d[r][c] + k0 * (d[r - 1][c] + d[r + 1][c]);
             else gx = __fmaf_rn(k0, d[r - 1][c] + d[r + 1][c], k1 * d[r][c]);
             const float gy = s[r + 1][c] - s[r - 1][c];
-            a += harris_f2d(gx * gx);
+            a += harris_f2d_nonneg(gx * gx);
             b += harris_f2d(gx * gy);
-            c2 += harris_f2d(gy * gy);
+            c2 += harris_f2d_nonneg(gy * gy);
         }
     const float A = (float)a, B = (float)b, C = (float)c2;
     if (!kFma) return (A * C - B * B) - (k * (A + C)) * (A + C);
