@@ -633,7 +633,7 @@ __device__ __forceinline__ F2 f2_sub(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %
 __device__ __forceinline__ F2 f2_set(float v) { return f2_pack(v, v); }
 __device__ __forceinline__ F2 f2_xor(F2 a, unsigned long long m) { F2 r; r.v = a.v ^ m; return r; }
 
-template <bool kFma, bool BORDER>
+template <bool kFma, bool BORDER, bool kIntF2D>
 __device__ __forceinline__ void harris_strip3(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0w, int hr_rows, int gl_lanes,
                                               int n_groups, float k, const DetectScratch &det, int b, unsigned long long *buf, unsigned *cnt) {
     const int lane = threadIdx.x & 31;
@@ -722,10 +722,17 @@ __device__ __forceinline__ void harris_strip3(const uint8_t *__restrict__ org, i
         // ---- Sobel row terms of this row (ring slot R0): pair E has taps (Pa, Pb, Pc), pair O has (Pb, Pc, Pd)
         dE[R0] = f2_sub(Pc, Pa);
         dO[R0] = f2_sub(Pd, Pb);
+        // ptxas (12.9) contracts a packed multiply feeding a packed add into FFMA2 even for explicit .rn operations and with
+        // -fmad=false (scalar mul.rn / add.rn are respected), so wherever the reference rounds a product before adding
+        // it the multiplies are packed and the ADDS are scalar.
         const F2 k0a = f2_mul(K0, Pa), k0b = f2_mul(K0, Pb), k0c = f2_mul(K0, Pc), k0d = f2_mul(K0, Pd);
         if (!kFma) {
-            sE[R0] = f2_add(f2_add(k0a, f2_mul(K1, Pb)), k0c);
-            sO[R0] = f2_add(f2_add(k0b, f2_mul(K1, Pc)), k0d);
+            const F2 k1b = f2_mul(K1, Pb), k1c = f2_mul(K1, Pc);
+            float a0, a1, b0, b1, c0_, c1, d0, d1, m0, m1, n0, n1;
+            f2_unpack(k0a, a0, a1); f2_unpack(k0b, b0, b1); f2_unpack(k0c, c0_, c1); f2_unpack(k0d, d0, d1);
+            f2_unpack(k1b, m0, m1); f2_unpack(k1c, n0, n1);
+            sE[R0] = f2_pack(__fadd_rn(__fadd_rn(a0, m0), c0_), __fadd_rn(__fadd_rn(a1, m1), c1));
+            sO[R0] = f2_pack(__fadd_rn(__fadd_rn(b0, n0), d0), __fadd_rn(__fadd_rn(b1, n1), d1));
         } else {
             sE[R0] = f2_fma(K0, Pc, f2_fma(K1, Pb, k0a));
             sO[R0] = f2_fma(K0, Pd, f2_fma(K1, Pc, k0b));
@@ -749,8 +756,11 @@ __device__ __forceinline__ void harris_strip3(const uint8_t *__restrict__ org, i
         const bool bflipy = BORDER && ((pr < 0) || (pr >= H));
         F2 gxE, gxO;
         if (!kFma) {
-            gxE = f2_add(f2_mul(K1, dE[R2]), f2_mul(K0, f2_add(dE[R1], dE[R0])));
-            gxO = f2_add(f2_mul(K1, dO[R2]), f2_mul(K0, f2_add(dO[R1], dO[R0])));
+            const F2 uE = f2_mul(K0, f2_add(dE[R1], dE[R0])), vE = f2_mul(K1, dE[R2]);
+            const F2 uO = f2_mul(K0, f2_add(dO[R1], dO[R0])), vO = f2_mul(K1, dO[R2]);
+            float u0, u1, v0, v1;
+            f2_unpack(uE, u0, u1); f2_unpack(vE, v0, v1); gxE = f2_pack(__fadd_rn(v0, u0), __fadd_rn(v1, u1));
+            f2_unpack(uO, u0, u1); f2_unpack(vO, v0, v1); gxO = f2_pack(__fadd_rn(v0, u0), __fadd_rn(v1, u1));
         } else {
             gxE = f2_fma(K0, f2_add(dE[R1], dE[R0]), f2_mul(K1, dE[R2]));
             gxO = f2_fma(K0, f2_add(dO[R1], dO[R0]), f2_mul(K1, dO[R2]));
@@ -761,12 +771,16 @@ __device__ __forceinline__ void harris_strip3(const uint8_t *__restrict__ org, i
         const F2 faE = f2_mul(gxE, gxE), faO = f2_mul(gxO, gxO), fcE = f2_mul(gyE, gyE), fcO = f2_mul(gyO, gyO);
         {
             float e0, e1;
-            f2_unpack(faE, e0, e1); qa[R0][0] = (double)e0; qa[R0][2] = (double)e1;
-            f2_unpack(faO, e0, e1); qa[R0][1] = (double)e0; qa[R0][3] = (double)e1;
-            f2_unpack(fbE, e0, e1); qb[R0][0] = (double)e0; qb[R0][2] = (double)e1;
-            f2_unpack(fbO, e0, e1); qb[R0][1] = (double)e0; qb[R0][3] = (double)e1;
-            f2_unpack(fcE, e0, e1); qc[R0][0] = (double)e0; qc[R0][2] = (double)e1;
-            f2_unpack(fcO, e0, e1); qc[R0][1] = (double)e0; qc[R0][3] = (double)e1;
+            // float -> double: F2F.F64.F32 runs at ~5 results / clk / SM and bounds the kernel; the integer re-biasing
+            // (harris_exact.cuh) moves it to the ALU pipe
+            auto cv = [](float f) { return kIntF2D ? harris_f2d(f) : (double)f; };
+            auto cvn = [](float f) { return kIntF2D ? harris_f2d_nonneg(f) : (double)f; };
+            f2_unpack(faE, e0, e1); qa[R0][0] = cvn(e0); qa[R0][2] = cvn(e1);
+            f2_unpack(faO, e0, e1); qa[R0][1] = cvn(e0); qa[R0][3] = cvn(e1);
+            f2_unpack(fbE, e0, e1); qb[R0][0] = cv(e0); qb[R0][2] = cv(e1);
+            f2_unpack(fbO, e0, e1); qb[R0][1] = cv(e0); qb[R0][3] = cv(e1);
+            f2_unpack(fcE, e0, e1); qc[R0][0] = cvn(e0); qc[R0][2] = cvn(e1);
+            f2_unpack(fcO, e0, e1); qc[R0][1] = cvn(e0); qc[R0][3] = cvn(e1);
         }
         double va[6], vb[6], vc[6];
 #pragma unroll
@@ -791,10 +805,15 @@ __device__ __forceinline__ void harris_strip3(const uint8_t *__restrict__ org, i
             const F2 A01 = f2_pack(A[0], A[1]), A23 = f2_pack(A[2], A[3]), B01 = f2_pack(B[0], B[1]), B23 = f2_pack(B[2], B[3]);
             const F2 C01 = f2_pack(C[0], C[1]), C23 = f2_pack(C[2], C[3]);
             const F2 T01 = f2_add(A01, C01), T23 = f2_add(A23, C23);
-            const F2 D01 = f2_sub(f2_mul(A01, C01), f2_mul(B01, B01)), D23 = f2_sub(f2_mul(A23, C23), f2_mul(B23, B23));
-            F2 r01, r23;
-            if (!kFma) { r01 = f2_sub(D01, f2_mul(f2_mul(KK, T01), T01)); r23 = f2_sub(D23, f2_mul(f2_mul(KK, T23), T23)); }
-            else { r01 = f2_sub(D01, f2_mul(KK, f2_mul(T01, T01))); r23 = f2_sub(D23, f2_mul(KK, f2_mul(T23, T23))); }
+            // products packed, differences scalar (see above: a packed product must not feed a packed add)
+            const F2 ac01 = f2_mul(A01, C01), ac23 = f2_mul(A23, C23), bb01 = f2_mul(B01, B01), bb23 = f2_mul(B23, B23);
+            const F2 kt01 = kFma ? f2_mul(KK, f2_mul(T01, T01)) : f2_mul(f2_mul(KK, T01), T01);
+            const F2 kt23 = kFma ? f2_mul(KK, f2_mul(T23, T23)) : f2_mul(f2_mul(KK, T23), T23);
+            float x0_, x1_, y0_, y1_, z0_, z1_;
+            f2_unpack(ac01, x0_, x1_); f2_unpack(bb01, y0_, y1_); f2_unpack(kt01, z0_, z1_);
+            F2 r01 = f2_pack(__fsub_rn(__fsub_rn(x0_, y0_), z0_), __fsub_rn(__fsub_rn(x1_, y1_), z1_));
+            f2_unpack(ac23, x0_, x1_); f2_unpack(bb23, y0_, y1_); f2_unpack(kt23, z0_, z1_);
+            F2 r23 = f2_pack(__fsub_rn(__fsub_rn(x0_, y0_), z0_), __fsub_rn(__fsub_rn(x1_, y1_), z1_));
             if (BORDER) {
                 // dilate ignores pixels outside the image: -inf there (v + 0 is exact, v - inf = -inf)
                 const float rinv = (q < 0 || q >= H) ? -INFINITY : 0.0f;
@@ -850,7 +869,7 @@ __device__ __forceinline__ void harris_strip3(const uint8_t *__restrict__ org, i
     if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
 }
 
-template <bool kFma>
+template <bool kFma, bool kIntF2D>
 __global__ void __launch_bounds__(HW_WARPS * 32)
 harris_nms3_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, int tiles_x, int strips, int gl_narrow, int n_items, int hr_rows) {
     __shared__ unsigned long long s_buf[HW_WARPS][HW_BUF];
@@ -870,8 +889,8 @@ harris_nms3_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, int 
         if (lane == 0) s_cnt[warp] = 0u;
         __syncwarp();
         const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
-        if (interior) harris_strip3<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, k, det, b, s_buf[warp], &s_cnt[warp]);
-        else harris_strip3<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, k, det, b, s_buf[warp], &s_cnt[warp]);
+        if (interior) harris_strip3<kFma, false, kIntF2D>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, k, det, b, s_buf[warp], &s_cnt[warp]);
+        else harris_strip3<kFma, true, kIntF2D>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, k, det, b, s_buf[warp], &s_cnt[warp]);
     }
 }
 
@@ -932,10 +951,12 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
         return 3;
     }
     if (!d_response && harris_impl() == 3) {
-        if (p.harris_fma)
-            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms3_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
-        else
-            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms3_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        // RDFE_HARRIS_F2D=0: hardware F2F for float -> double (the conversion unit then bounds the kernel)
+        static const bool intcv = [] { const char *e = getenv("RDFE_HARRIS_F2D"); return !(e && e[0] == '0'); }();
+#define RDFE_H3(FMA, CV) RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms3_kernel<FMA, CV><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, tiles_x, strips, gl_narrow, n_items, hr_rows)))
+        if (p.harris_fma) { if (intcv) RDFE_H3(true, true); else RDFE_H3(true, false); }
+        else { if (intcv) RDFE_H3(false, true); else RDFE_H3(false, false); }
+#undef RDFE_H3
         return 2;
     }
     if (p.harris_fma)

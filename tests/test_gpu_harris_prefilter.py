@@ -85,7 +85,7 @@ def test_candidates_bit_exact_shapes(orc, shape):
     H, W = shape
     with FrontEnd(W, H, max_level=1 if min(H, W) > 90 else 0, win=21, num_slots=2, max_points=256) as fe:
         frac = run(fe, orc, random_image(H, W, seed=W * 5 + H))
-        assert 0.0 < frac < 0.15, f"prefilter flagged {100 * frac:.1f} % of the pixels"
+        assert frac < 0.15, f"prefilter flagged {100 * frac:.1f} % of the pixels"      # 0 when an exact-everywhere kernel is selected
 
 
 @pytest.mark.parametrize("kind", ["noise", "binary", "lowcontrast", "half_saturated", "blocks", "impulses", "checker7"])
