@@ -904,11 +904,17 @@ static bool harris_narrow_enabled() {
     static const bool v = [] { const char *e = getenv("RDFE_HARRIS_NARROW"); return !(e && e[0] == '0'); }();
     return v;
 }
-// RDFE_HARRIS_IMPL: 3 (default) = packed exact kernel harris_nms3_kernel; 0 = the round-1 exact kernel harris_nms_kernel;
-// 1 = integer prefilter + exact evaluation of the flagged pixels (harris_flag_kernel / harris_resolve_kernel).  All three
-// emit identical keys (tests/test_gpu_harris_prefilter.py runs each).
+// RDFE_HARRIS_IMPL selects one of three implementations that emit identical keys (tests/test_gpu_harris_prefilter.py and the
+// detect / golden / cv2 tests pass with each; measured on B200, 64 frames of 752x480, profiles/r2_harris_variants.md):
+//   0 (default) harris_nms_kernel: exact float64 chain at every pixel.  75.4 M warp instructions, 127 us.
+//   1 harris_flag_kernel + harris_resolve_kernel: integer prefilter, exact chain at the ~6.7 % flagged pixels only.
+//     41.2 M + 33 M warp instructions, 82 + 60 us: an isolated exact evaluation costs ~600 instructions against ~90 per
+//     pixel inside the rolling kernel, so the prefilter only pays below ~6 % flagged pixels (CLAHE output is above).
+//   3 harris_nms3_kernel: the exact chain with packed FADD2/FMUL2, ring-3 unrolling, FMNMX3.  60 M warp instructions
+//     (-20 %) but 151 us: all three are bound by dependent-issue latency at 12 warps per SM (eligible warps 0.6-1.1 per
+//     scheduler), not by issue slots or any pipe (alu 41 %, xu 34 %, fma 21 %, fp64 16 % for impl 0).
 static int harris_impl() {
-    static const int v = [] { const char *e = getenv("RDFE_HARRIS_IMPL"); const int r = e ? atoi(e) : 3; return (r == 0 || r == 1) ? r : 3; }();
+    static const int v = [] { const char *e = getenv("RDFE_HARRIS_IMPL"); const int r = e ? atoi(e) : 0; return (r == 1 || r == 3) ? r : 0; }();
     return v;
 }
 
