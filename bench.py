@@ -52,6 +52,11 @@ def parse():
                     help="also run cv::undistort's remap in front of preprocess (SURVEY 8(f) rank 1; not the headline config)")
     ap.add_argument("--profile-steps", type=int, default=20, help="extra steps with per-kernel events")
     ap.add_argument("--timeline", default="", help="write a per-launch timeline of 8 pipelined steps to this JSON file")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short BASELINE configs[2] (ADVIO-shaped) and configs[3] (1080p / 31x31) measurements")
+    ap.add_argument("--other-steps", type=int, default=30, help="timed steps of each other_configs measurement")
+    ap.add_argument("--no-compaction", action="store_true",
+                    help="round-1 step semantics (lost tracks stay in the keypoint list); default = the reference's (frame.cpp:160-170)")
     return ap.parse_args()
 
 
@@ -135,7 +140,10 @@ def run_cpu(args, wl, stream_ids, steps, warmup, budget_s=None, single_stream=Fa
                 "kind": "reference" if backend == "cv2" else "port",
                 "sample": f"{len(times)} steps x {len(stream_ids)} streams = {len(times) * len(stream_ids)} frames of the same "
                           f"synthetic workload, {pool.workers} worker processes x 1 OpenCV thread "
-                          f"({'cv2 ' + __import__('cv2').__version__ if backend == 'cv2' else 'C oracle port'})",
+                          f"({'cv2 ' + __import__('cv2').__version__ if backend == 'cv2' else 'C oracle port'}); "
+                          "bias: through Python cv2 the LK calls take level-0 images, so OpenCV rebuilds 4 pyramids + 2 Scharr sets "
+                          "per frame that the C++ reference would reuse (measured ~2.8 of 24 ms at 1 thread) and the CLAHE/GFTT "
+                          "objects are constructed per call: the arm is <= ~12 % pessimistic",
                 "ms_per_step": 1e3 * total / len(times), "steps": len(times)}
     finally:
         pool.close()
@@ -162,48 +170,50 @@ def main_reference(args, wl):
 
 
 def workload_config(args, wl, n_gpus):
-    return {"workload": f"BASELINE configs[1]: {wl['width']}x{wl['height']} u8, {args.streams} independent streams per GPU "
+    name = {"euroc": "BASELINE configs[1]", "advio": "BASELINE configs[2] (per-GPU share)", "hd": "BASELINE configs[3]"}.get(args.workload, args.workload)
+    return {"workload": f"{name}: {wl['width']}x{wl['height']} u8, {args.streams} independent streams per GPU "
                         f"batched per launch, {wl['points']} carried keypoints + {wl['points']}-point detect, maxLevel "
                         f"{wl['max_level']} ({wl['max_level'] + 1} images), {wl['win']}x{wl['win']} LK window, CLAHE 6.0/8x8, "
                         f"Harris-GFTT q=1e-3 minDist 20, Poisson radius 20, LK (30, 0.01)",
             "streams_per_gpu": args.streams, "global_streams": args.streams * n_gpus, "ring_frames": args.ring,
             "parallelism": f"streams partitioned across {n_gpus} GPU(s), no collective",
             "undistort": bool(getattr(args, "undistort", False)),
+            "step_semantics": "round-1 (lost tracks kept)" if getattr(args, "no_compaction", False) else
+                              "reference: only status != 0 points are carried into detect (frame.cpp:160-170)",
             "l2": f"inputs larger than L2: {args.streams}x{args.ring} resident frames = "
                   f"{args.streams * args.ring * wl['width'] * wl['height'] / 1e6:.0f} MB cycled (L2 126 MB)"}
 
 
 # --------------------------------------------------------------------------- GPU arm
-def main_b200(args, wl):
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    stream_ids = [rank * args.streams + i for i in range(args.streams)]
-    # frame rings: generated once per box, before CUDA is touched
-    WL.ensure_rings(stream_ids, wl["width"], wl["height"], args.ring,
-                    workers=max(1, (os.cpu_count() or 1) // max(world, 1)))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        # NCCL only reduces timing scalars here (streams share no state).  Its start-up banner goes to stdout,
-        # which must carry exactly one JSON line: point fd 1 at stderr while the communicator comes up.
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
+CONFIG_NAMES = {"euroc": "BASELINE configs[1]", "advio": "BASELINE configs[2] (per-GPU share)", "hd": "BASELINE configs[3]"}
+
+
+def ncu_counters(workload, S):
+    """Per-launch counters of the committed ncu launch list of this workload (profiles/r2_traffic.json, made by
+    scripts/make_traffic.py): DRAM bytes, warp instructions, shared-memory wavefronts.  None when not captured."""
+    if workload != "euroc" or S != 64:
+        return {}
+    for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+            return json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"]
+        except Exception:
+            continue
+    return {}
+
+
+def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e, want_timeline=""):
+    """One workload on this rank's GPU: device-resident value, per-kernel times, e2e + copy-only legs."""
+    import torch
     from rd_vio_b200 import _native as N
+    from rd_vio_b200 import parallel as PAR
     from rd_vio_b200.frontend import FrontEnd
     from rd_vio_b200.synthetic import SyntheticStream
+    rank, world, local, dist = env["rank"], env["world"], env["local"], env["dist"]
+    wl = WL.WORKLOADS[wl_name]
+    stream_ids = PAR.partition_streams(rank, world, S)
+    WL.ensure_rings(stream_ids, wl["width"], wl["height"], T, workers=max(1, (os.cpu_count() or 1) // max(world, 1)))
     L = N.lib()
-    W, H, NP, T, S = wl["width"], wl["height"], wl["points"], args.ring, args.streams
+    W, H, NP = wl["width"], wl["height"], wl["points"]
     stride = 2 * NP
     # a real (non-default) stream shared by torch (copies, events) and the library (kernels): the legacy
     # default stream has handle 0, which the C ABI reads as "create your own"
@@ -218,6 +228,7 @@ def main_b200(args, wl):
     slots = [np.array([fe.acquire() for _ in range(S)], np.int32) for _ in range(NSETS)]
     slotsA = slots[0]
     N.check(L.rdfe_set_pipelining(h, 1), "set_pipelining")
+    N.check(L.rdfe_set_step_compaction(h, 0 if args.no_compaction else 1), "set_step_compaction")
     if args.undistort:
         sc = W / 752.0
         fe.set_undistort(np.array([[458.654 * sc, 0, 367.215 * sc], [0, 457.296 * sc, 248.375 * H / 480.0], [0, 0, 1]], np.float32),
@@ -286,7 +297,7 @@ def main_b200(args, wl):
     sampler = ClockSampler(local)
     sampler.start()                      # clocks are sampled under load: warm-up + timed region
     w0 = time.perf_counter()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_dev(t); t += 1
     torch.cuda.synchronize()
     while time.perf_counter() - w0 < 0.8:   # extra untimed warm-up so nvidia-smi (100 ms period) sees the load
@@ -297,54 +308,57 @@ def main_b200(args, wl):
     launches0 = fe.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_dev(t); t += 1
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = fe.kernel_launches() - launches0
-    tracked_ok = float(status[:, :NP].float().mean().item())
+    # last step's LK flags, masked by that step's counts (entries beyond a stream's count are stale)
+    k_last = (t - 1) % T
+    live = torch.arange(stride, device="cuda")[None, :] < cnt[k_last][:, None]
+    n_tracked = float((status.bool() & live).sum().item())
+    tracked_ok = n_tracked / max(float(cnt_h[k_last].sum()), 1.0)
+    new_per_frame = float(work_cnt.float().mean().item()) - n_tracked / S if not args.no_compaction else None
     fe.sync()   # also surfaces a candidate-buffer overflow
-    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
-    value = world * S * args.steps / (ms_max * 1e-3)
+    # whole-job frames/s = frames of all ranks / MAX over ranks of the device time (rd_vio_b200/parallel.py)
+    value, ms_max = PAR.aggregate_throughput(S * steps, ms, dist, torch.device("cuda", local))
 
     # ---- per-kernel device time (separate pass, events around every launch) -> roofline of the dominant kernel
     prof = None
-    if rank == 0 and args.profile_steps > 0:
+    if rank == 0 and profile_steps > 0:
         N.check(L.rdfe_profile_enable(h, 1), "profile_enable")
-        for _ in range(args.profile_steps):
+        for _ in range(profile_steps):
             step_dev(t); t += 1
         nk = L.rdfe_profile_num_kernels()
         pms = (C.c_double * nk)(); pn = (C.c_int64 * nk)()
         N.check(L.rdfe_profile_collect(h, pms, pn), "profile_collect")
         N.check(L.rdfe_profile_enable(h, 0), "profile_enable")
-        prof = {L.rdfe_profile_kernel_name(i).decode(): {"ms_per_step": pms[i] / args.profile_steps,
-                                                        "launches_per_step": pn[i] / args.profile_steps,
+        prof = {L.rdfe_profile_kernel_name(i).decode(): {"ms_per_step": pms[i] / profile_steps,
+                                                        "launches_per_step": pn[i] / profile_steps,
                                                         "us_per_launch": 1e3 * pms[i] / max(pn[i], 1)} for i in range(nk)}
-    elif args.profile_steps > 0:
-        for _ in range(args.profile_steps):
+        prof = {k: v for k, v in prof.items() if v["launches_per_step"] > 0}
+    elif profile_steps > 0:
+        for _ in range(profile_steps):
             step_dev(t); t += 1
         fe.sync()
 
-    if rank == 0 and args.timeline:
+    if rank == 0 and want_timeline:
         N.check(L.rdfe_profile_enable(h, 2), "profile_enable")
         for _ in range(10):
             step_dev(t); t += 1
         cap = 1024
-        kid = (C.c_int * cap)(); t0s = (C.c_float * cap)(); t1s = (C.c_float * cap)(); cnt = C.c_int(0)
-        N.check(L.rdfe_profile_timeline(h, kid, t0s, t1s, cap, C.byref(cnt)), "profile_timeline")
+        kid = (C.c_int * cap)(); t0s = (C.c_float * cap)(); t1s = (C.c_float * cap)(); ncap = C.c_int(0)
+        N.check(L.rdfe_profile_timeline(h, kid, t0s, t1s, cap, C.byref(ncap)), "profile_timeline")
         N.check(L.rdfe_profile_enable(h, 0), "profile_enable")
-        with open(args.timeline, "w") as f:
+        with open(want_timeline, "w") as f:
             json.dump([{"kernel": L.rdfe_profile_kernel_name(kid[i]).decode(), "start_us": round(1e3 * t0s[i], 2),
-                        "end_us": round(1e3 * t1s[i], 2)} for i in range(cnt.value)], f)
+                        "end_us": round(1e3 * t1s[i], 2)} for i in range(ncap.value)], f)
 
     # ---- end to end through the host-pointer C ABI: pinned host frames + keypoints in, results out, every step
     e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         h_curr = torch.from_numpy(curr_h).pin_memory().numpy()
         h_pred = torch.from_numpy(pred_h).pin_memory().numpy()
         h_cnt = cnt_h.copy()
@@ -366,7 +380,7 @@ def main_b200(args, wl):
 
         h2d = S * H * W + 2 * S * stride * 16 + 2 * S * 4
         d2h = S * stride * 16 + S * 4 + S * stride + 4
-        e_steps = max(10, min(args.steps, 200))
+        e_steps = max(10, min(steps, 200))
         tk = submit(t); t += 1
         for _ in range(3):                       # warm the pipeline
             tk2 = submit(t); t += 1
@@ -381,72 +395,180 @@ def main_b200(args, wl):
         wait(tk)
         barrier()
         sec = time.perf_counter() - w0
-        sec_t = torch.tensor([sec], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(sec_t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * S * e_steps / float(sec_t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+        e_value, sec_max_ms = PAR.aggregate_throughput(S * e_steps, sec * 1e3, dist, torch.device("cuda", local))
+        # copy-only leg: the same pinned frames through the same upload path (rdfe_upload_only: same staging, copy
+        # stream and single 2-D copy as submit), no kernels -- what this box's host side delivers to N GPUs at once
+        fe.sync()
+        for tt in range(3):
+            N.check(L.rdfe_upload_only(h, slots[tt % NSETS].ctypes.data, S, hptrs[tt % T], W, 1), "upload_only")
+        barrier()
+        w0 = time.perf_counter()
+        for tt in range(e_steps):
+            N.check(L.rdfe_upload_only(h, slots[tt % NSETS].ctypes.data, S, hptrs[tt % T], W, 1 if tt == e_steps - 1 else 0),
+                    "upload_only")
+        barrier()
+        csec = time.perf_counter() - w0
+        c_value, _ = PAR.aggregate_throughput(S * e_steps, csec * 1e3, dist, torch.device("cuda", local))
+        e2e = {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "steps": e_steps,
+               "h2d_gbs_in_e2e": e_value * H * W / 1e9,
+               "h2d_only": {"frames_per_s": c_value, "gbs_all_gpus": c_value * H * W / 1e9, "gbs_per_gpu": c_value * H * W / 1e9 / world,
+                            "e2e_over_copy_only": e_value / c_value if c_value > 0 else None,
+                            "how": "rdfe_upload_only: the frame uploads of the same steps alone (same pinned buffers, same "
+                                   "staging, copy stream and one strided 2-D copy per step), no kernels, all ranks at once"},
                "how": "rdfe_frontend_step_submit/_wait (C ABI, pinned HOST buffers, two steps in flight): every step "
-                      "copies its 64 frames + carried keypoints + predictions H2D and its tracked/detected keypoints, "
+                      f"copies its {S} frames + carried keypoints + predictions H2D and its tracked/detected keypoints, "
                       "counts and status D2H; wall clock bracketed by barrier+synchronize, max over ranks"}
 
-    if rank != 0:
-        fe.close()
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+    out = {"workload": wl_name, "wl": wl, "S": S, "T": T, "steps": steps, "warmup": max(warmup, 3), "value": value, "ms_max": ms_max,
+           "launches": int(launches), "clocks": clocks, "prof": prof, "e2e": e2e, "mean_pts": mean_pts, "tracked_ok": tracked_ok,
+           "new_per_frame": new_per_frame, "stream_ids": stream_ids}
+    fe.close()
+    del dev_frames, host_frames, curr_xy, pred_xy
+    torch.cuda.empty_cache()
+    return out
 
-    # ---- roofline of the dominant kernel
-    hbm_peak, peak_src = peaks()
-    total_bytes, stage_bytes = WL.algorithmic_bytes(W, H, NP, wl["max_level"], wl["win"], undistort=bool(args.undistort))
+
+def annotate_kernels(m, hbm_peak, peak_src, sm_mhz):
+    """roofline of the dominant kernel + every kernel against the same HBM peak; LK is charged for the points the
+    run actually carried (mean_pts), not the nominal count."""
+    wl, S = m["wl"], m["S"]
+    W, H = wl["width"], wl["height"]
+    total_nominal, _ = WL.algorithmic_bytes(W, H, wl["points"], wl["max_level"], wl["win"])
+    total_bytes, stage_bytes = WL.algorithmic_bytes(W, H, m["mean_pts"], wl["max_level"], wl["win"])
+    prof = m["prof"]
+    counters = ncu_counters(m["workload"], S)
     roofline = None
     if prof:
-        dom = max(prof, key=lambda kname: prof[kname]["ms_per_step"])
-        per_launch_bytes = stage_bytes.get(dom, 0) * S / max(prof[dom]["launches_per_step"], 1)
-        ach = per_launch_bytes / (prof[dom]["us_per_launch"] * 1e-6) / 1e9 if prof[dom]["us_per_launch"] > 0 else 0.0
-        traffic = None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
-            for kname, v in tj.items():
-                if kname.startswith(dom) and args.workload == "euroc" and S == 64:
-                    traffic = v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]
-        except Exception:
-            traffic = None
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "note": "LK and Harris are instruction-issue-bound, not HBM-bound (ncu: profiles/, DESIGN.md section 4)",
-                    "algorithmic_bytes_per_launch": per_launch_bytes, "us_per_launch": prof[dom]["us_per_launch"],
-                    "share_of_step": prof[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in prof.values()), 1e-12)}
-    step_frac = (value / world) * total_bytes / 1e9 / hbm_peak
-    if prof:   # every kernel against the same HBM peak (algorithmic bytes of its stage / its serialised time)
+        f_hz = (sm_mhz or 1965.0) * 1e6
         for kname, v in prof.items():
             sb = stage_bytes.get(kname, 0) * S
             v["algorithmic_bytes_per_step"] = sb
             v["achieved_gbs"] = (sb / (v["ms_per_step"] * 1e-3) / 1e9) if v["ms_per_step"] > 0 else 0.0
             v["hbm_frac"] = v["achieved_gbs"] / hbm_peak
+            for cname, c in counters.items():
+                if cname.startswith(kname) and v["us_per_launch"] > 0:
+                    t_s = v["us_per_launch"] * 1e-6
+                    if c.get("warp_inst_per_launch"):
+                        # warp instructions / (4 schedulers x 148 SMs x clock x time): 1.0 = every issue slot used
+                        v["issue_frac"] = c["warp_inst_per_launch"] / (4 * 148 * f_hz * t_s)
+                    if c.get("smem_wavefronts_per_launch"):
+                        # shared-memory wavefronts / (1 per cycle per SM)
+                        v["smem_frac"] = c["smem_wavefronts_per_launch"] / (148 * f_hz * t_s)
+                    v["dram_bytes_per_launch_ncu"] = c.get("dram_read_bytes_per_launch", 0) + c.get("dram_write_bytes_per_launch", 0)
+        dom = max(prof, key=lambda kname: prof[kname]["ms_per_step"])
+        d = prof[dom]
+        per_launch_bytes = stage_bytes.get(dom, 0) * S / max(d["launches_per_step"], 1)
+        ach = per_launch_bytes / (d["us_per_launch"] * 1e-6) / 1e9 if d["us_per_launch"] > 0 else 0.0
+        bound = "hbm"
+        roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": d.get("dram_bytes_per_launch_ncu"), "peak_source": peak_src,
+                    "issue_frac": d.get("issue_frac"), "smem_frac": d.get("smem_frac"),
+                    "note": "the contract's bound is HBM (byte model of SURVEY.md 8(d)); the kernel itself is limited by "
+                            "instruction issue / dependent-latency chains, not by DRAM: issue_frac = warp instructions / "
+                            "(4 x 148 x SM clock x time) and smem_frac = shared-memory wavefronts / (148 x clock x time), "
+                            "counters from the committed ncu launch list (profiles/r2_traffic.json)",
+                    "algorithmic_bytes_per_launch": per_launch_bytes, "us_per_launch": d["us_per_launch"],
+                    "carried_points_charged": m["mean_pts"],
+                    "share_of_step": d["ms_per_step"] / max(sum(v["ms_per_step"] for v in prof.values()), 1e-12)}
+    world = m.get("world", 1)
+    step = {"algorithmic_bytes_per_frame": total_bytes, "algorithmic_bytes_per_frame_nominal_points": total_nominal,
+            "frac_per_gpu": (m["value"] / world) * total_bytes / 1e9 / hbm_peak, "peak_gbs": hbm_peak, "peak_source": peak_src}
+    return roofline, step
+
+
+def main_b200(args, wl):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        # NCCL only reduces timing scalars here (streams share no state).  Its start-up banner goes to stdout,
+        # which must carry exactly one JSON line: point fd 1 at stderr while the communicator comes up.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+    env = {"rank": rank, "world": world, "local": local, "dist": dist}
+    m = measure_gpu(args, env, args.workload, args.streams, args.ring, args.steps, args.warmup, args.profile_steps,
+                    not args.no_e2e, args.timeline)
+    m["world"] = world
+
+    # ---- BASELINE configs[2] / configs[3]: short measurements in the same process, every N (all ranks take part)
+    others = {}
+    if not args.no_other_configs and args.workload == "euroc":
+        for name, S2, T2 in (("advio", 32, 5), ("hd", 32, 4)):
+            try:
+                mo = measure_gpu(args, env, name, S2, T2, args.other_steps, 3, 8, False)
+                mo["world"] = world
+                others[name] = mo
+            except Exception as e:      # report, never hide; the headline line must still be printed
+                others[name] = {"error": repr(e)}
+                if dist is not None:
+                    raise
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    hbm_peak, peak_src = peaks()
+    roofline, step = annotate_kernels(m, hbm_peak, peak_src, m["clocks"].get("sm_mhz"))
+    other_cfgs = {}
+    for name, mo in others.items():
+        if "error" in mo:
+            other_cfgs[name] = mo
+            continue
+        r2, st2 = annotate_kernels(mo, hbm_peak, peak_src, mo["clocks"].get("sm_mhz"))
+        w2 = mo["wl"]
+        other_cfgs[name] = {
+            "config": CONFIG_NAMES[name] + f": {w2['width']}x{w2['height']}, {mo['S']} streams per GPU, {w2['points']} keypoints, "
+                      f"maxLevel {w2['max_level']}, {w2['win']}x{w2['win']} window, ring {mo['T']} frames (> L2)",
+            "value": mo["value"], "unit": UNIT, "n_gpus": world, "steps": mo["steps"], "warmup": mo["warmup"],
+            "ms_per_step": mo["ms_max"] / mo["steps"], "hbm_roofline_step": st2, "roofline": r2,
+            "kernels_us_per_launch": {k: round(v["us_per_launch"], 1) for k, v in (mo["prof"] or {}).items()},
+            "mean_carried_keypoints": mo["mean_pts"], "tracked_ok_frac": mo["tracked_ok"], "clocks": mo["clocks"]}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            cpu_streams = stream_ids[:min(S, 64)]
+            cpu_streams = m["stream_ids"][:min(args.streams, 64)]
             r = run_cpu(args, wl, cpu_streams, steps=40, warmup=1, budget_s=20.0)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:   # report, never hide
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
 
+    parity_report = None
+    try:    # committed disagreement table vs OpenCV's default (dispatched / FMA) mode, north_star's reporting clause
+        parity_report = json.load(open(os.path.join(ROOT, "profiles", "r2_disagreement.json")))["summary"]
+    except Exception:
+        parity_report = None
+
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": m["ms_max"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
         "config": workload_config(args, wl, world),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["launches"],
         "roofline": roofline, "cpu_baseline": cpu,
-        "hbm_roofline_step": {"algorithmic_bytes_per_frame": total_bytes, "frac_per_gpu": step_frac,
-                              "peak_gbs": hbm_peak, "peak_source": peak_src},
-        "kernels": prof, "mean_carried_keypoints": mean_pts, "tracked_ok_frac": tracked_ok,
+        "hbm_roofline_step": step,
+        "kernels": m["prof"], "mean_carried_keypoints": m["mean_pts"], "tracked_ok_frac": m["tracked_ok"],
+        "new_keypoints_per_frame": m["new_per_frame"],
+        "other_configs": other_cfgs,
+        "scope_note": "the step is the plugin's three calls; Frame::track_keypoints' two host RANSAC masks (frame.cpp:99-132, "
+                      "SURVEY 8(f) rank 2) between track and detect stay on the host and are NOT in the timed region of either arm",
+        "disagreement_vs_default_opencv": parity_report,
     }
     print(json.dumps(line), flush=True)
-    fe.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -77,6 +77,18 @@ class GpuFrontEnd {
         static size_t v = 0;
         return v;
     }
+    // FeatureTracker::run calls detect_keypoints only on sliding-window frames (feature_tracker.cpp:39-41,97: every
+    // frame until initialised, then every sliding_window_tracker_frequent-th).  The detection prefetch of preprocess()
+    // follows that rhythm: frames_since_detect() counts preprocess() calls since the last detect_keypoints(),
+    // detect_gap() is the count seen at that detect; a frame is prefetched only when it is expected to be detected.
+    static int &frames_since_detect() {
+        static int v = 0;
+        return v;
+    }
+    static int &detect_gap() {
+        static int v = 1;
+        return v;
+    }
     static rdfe_detect_params detect_params(size_t frozen) {
         rdfe_detect_params p;
         rdfe_default_detect_params(&p);
@@ -117,7 +129,8 @@ class GpuImage : public Image {
         // FeatureTracker calls track(prev -> this) and then detect(this) (feature_tracker.cpp:43-96).  Corner
         // selection needs neither the tracked points nor the pyramid levels above 0, so once the detector's
         // parameters are frozen it is started here and runs beside the tracking call.
-        if (const size_t frozen = GpuFrontEnd::frozen_max_points()) {
+        const bool detect_expected = ++GpuFrontEnd::frames_since_detect() == GpuFrontEnd::detect_gap();
+        if (const size_t frozen = detect_expected ? GpuFrontEnd::frozen_max_points() : 0) {
             const rdfe_detect_params p = GpuFrontEnd::detect_params(frozen);
             rdfe_detect_prefetch(ctx_, &slot_, 1, &p);      // optional: a failure only means detect does the work itself
         }
@@ -128,6 +141,8 @@ class GpuImage : public Image {
         // static singleton semantics of OpenCvImage::gftt (opencv_image.cpp:184-188)
         size_t &frozen = GpuFrontEnd::frozen_max_points();
         if (frozen == 0) frozen = max_points ? max_points : 4096;
+        if (GpuFrontEnd::frames_since_detect() > 0) GpuFrontEnd::detect_gap() = GpuFrontEnd::frames_since_detect();
+        GpuFrontEnd::frames_since_detect() = 0;
         if (!ctx_ || slot_ < 0) return;
         rdfe_detect_params p = GpuFrontEnd::detect_params(frozen);
         p.keypoint_distance = keypoint_distance;

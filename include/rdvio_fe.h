@@ -52,7 +52,7 @@ typedef enum rdfe_status {
     RDFE_ERR_NOMEM = -3,
     RDFE_ERR_NOSLOT = -4,        /* slot pool exhausted */
     RDFE_ERR_UNSUPPORTED = -5,   /* e.g. LK window other than 21 or 31 */
-    RDFE_ERR_OVERFLOW = -6       /* corner-candidate buffer overflow */
+    RDFE_ERR_OVERFLOW = -6       /* corner-candidate buffer overflow, or keypoints beyond `stride` were dropped */
 } rdfe_status;
 
 typedef struct rdfe_ctx rdfe_ctx;
@@ -123,7 +123,8 @@ RDFE_API int rdfe_preprocess_batch_dev(rdfe_ctx *ctx, const int *slots, int n,
 /* ---- OpenCvImage::detect_keypoints (opencv_image.cpp:38-73) ------------- */
 /* keypoints_xy: [n][stride][2] doubles; counts[i] existing keypoints on entry
  * (they preset the Poisson-disk filter), new ones are appended and counts[i]
- * updated (never beyond `stride`).  gftt_* (optional, may be NULL) receive the
+ * updated.  The reference's vector is unbounded: if existing + new exceed `stride` the
+ * list is cut there and the next synchronising call returns RDFE_ERR_OVERFLOW.  gftt_* (optional, may be NULL) receive the
  * raw GFTT corners [n][max_points][2] float, responses, and counts. */
 RDFE_API int rdfe_detect_batch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_params *p,
                       double *keypoints_xy, int *counts, int stride,
@@ -159,9 +160,15 @@ RDFE_API int rdfe_track_batch_dev(rdfe_ctx *ctx, const int *curr_slots, const in
 
 /* ---- one call per new frame: FeatureTracker::run's plugin sequence (feature_tracker.cpp:32-98) ----
  * preprocess(new) -> track_keypoints(prev -> new) -> detect_keypoints(new), device pointers, asynchronous.
- * dev_next_xy [n][stride][2]: prediction in (if tp->has_prediction), tracked result out (status != 0 only),
- * then used as detect's existing keypoints: dev_kp_counts[i] entries on entry, new corners appended and
- * dev_kp_counts[i] updated.  prev_slots == NULL (first frame of a stream) skips the tracking stage.
+ * dev_next_xy [n][stride][2]: prediction in (if tp->has_prediction), tracked result out (status != 0 only).
+ * Then, as Frame::track_keypoints does before the new frame sees detect (frame.cpp:160-170: only status != 0
+ * points are appended to the next frame), the list is compacted in order to the tracked points
+ * (rdfe_set_step_compaction, default on; dev_status keeps the original indexing: entry i of the input is entry
+ * rank(i) of the output), and those are detect's existing keypoints: new corners are appended and
+ * dev_kp_counts[i] = tracked + new (on entry: the number of carried points = dev_track_counts[i]).  The two
+ * host-side RANSAC masks of frame.cpp:99-132 sit between track and detect in the reference; a caller that wants
+ * them uses the separate calls (or ANDs its mask into dev_status on the context's stream before this call's
+ * Poisson stage -- not offered here).  prev_slots == NULL (first frame of a stream) skips the tracking stage.
  * After CLAHE the detection branch (Harris + GFTT selection, which need only level 0) runs on an internal second
  * stream concurrently with the tracking branch (pyramid, Scharr, LK); only the Poisson-disk append joins both. */
 RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
@@ -195,17 +202,26 @@ RDFE_API int rdfe_set_input_format(rdfe_ctx *ctx, int channels);
  * created with a high priority keeps its own small copies from queueing behind the large grids. */
 RDFE_API int rdfe_set_pipelining(rdfe_ctx *ctx, int on);
 
+/* Fused step only: on (default) = lost tracks (status == 0) are dropped before detect, the reference's behaviour
+ * (frame.cpp:160-170); off = every carried entry (prediction where tracking failed) stays in the list and keeps
+ * suppressing new corners -- the round-1 behaviour, kept for A/B measurements. */
+RDFE_API int rdfe_set_step_compaction(rdfe_ctx *ctx, int on);
+
 /* Host-buffer form of the same step, pipelined two deep: submit() uploads the frames and keypoints on a copy
  * stream and enqueues the step; wait() blocks until that step's results are on the host and copies them out.
  * submit(t+1) may precede wait(t) so that the upload of the next frames overlaps the kernels of the current
  * step.  next_xy [n][stride][2]: positions of the carried keypoints (prediction where tracking failed) followed
- * by the newly detected corners, kp_counts[i] entries; status [n][stride].  pred_xy may be NULL (seed with
+ * by the newly detected corners (with step compaction, the default: only the tracked ones, in order, followed by
+ * the new corners), kp_counts[i] entries; status [n][stride] in the input's indexing.  pred_xy may be NULL (seed with
  * curr_xy); prev_slots may be NULL (no tracking, counts[i] existing keypoints are taken from curr_xy = NULL -> 0). */
 RDFE_API int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
                               const uint8_t *const *images, size_t pitch, double clip_limit, int tiles_x, int tiles_y,
                               const rdfe_track_params *tp, const double *curr_xy, const double *pred_xy, const int *counts,
                               const rdfe_detect_params *dp, int stride, int *ticket);
 RDFE_API int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy, int *kp_counts, char *status);
+/* Measurement aid: only the frame upload of rdfe_frontend_step_submit (same staging, copy stream and copy shape),
+ * no kernels; sync != 0 waits for the copy stream.  bench.py times it alone ("h2d_only") next to the e2e number. */
+RDFE_API int rdfe_upload_only(rdfe_ctx *ctx, const int *new_slots, int n, const uint8_t *const *images, size_t pitch, int sync);
 
 /* ---- parity / debugging taps (not on the hot path) ---------------------- */
 /* plane: 0 = 8-bit image (w*h bytes), 1 = Scharr derivative (w*h*2 int16),

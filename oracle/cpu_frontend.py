@@ -69,7 +69,7 @@ class _StreamState:
         k = t % self.ring
         new = self._pre(self.frames[(k + 1) % self.ring])
         nxt, st = self._track(self.prev, new, self.kp[k], self.pred[k])
-        out = self._detect(new, nxt)
+        out = self._detect(new, nxt[np.asarray(st) != 0])     # frame.cpp:160-170: only tracked points are carried
         self.prev = new
         self.last = (nxt, st, out)
 

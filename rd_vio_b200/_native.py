@@ -59,9 +59,11 @@ SYMBOLS = {
     "rdfe_set_undistort": (_i, [_vp, _vp, _vp]),
     "rdfe_set_input_format": (_i, [_vp, _i]),
     "rdfe_set_pipelining": (_i, [_vp, _i]),
+    "rdfe_set_step_compaction": (_i, [_vp, _i]),
     "rdfe_frontend_step_submit": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _d, _i, _i, C.POINTER(TrackParams), _vp, _vp, _vp,
                                        C.POINTER(DetectParams), _i, C.POINTER(_i)]),
     "rdfe_frontend_step_wait": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "rdfe_upload_only": (_i, [_vp, _vp, _i, _vp, _sz, _i]),
     "rdfe_download_level": (_i, [_vp, _i, _i, _i, _vp, _sz]),
     "rdfe_download_clahe_lut": (_i, [_vp, _i, _vp, _sz]),
     "rdfe_upload_level0": (_i, [_vp, _i, _vp, _sz]),

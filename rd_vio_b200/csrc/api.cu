@@ -120,8 +120,8 @@ static int make_clahe_params(const rdfe_ctx *ctx, double clip_limit, int tiles_x
 }
 
 static int check_slots(const rdfe_ctx *ctx, const int *slots, int n, SlotList *out, const char *what) {
-    if (!ctx || !slots || n < 1 || n > RDFE_MAX_BATCH) {
-        set_error("%s: batch size %d out of range [1,%d]", what, n, RDFE_MAX_BATCH);
+    if (!ctx || !slots || n < 1 || n > ctx->max_batch) {
+        set_error("%s: batch size %d out of range [1,%d] (min(num_slots, RDFE_MAX_BATCH))", what, n, ctx ? ctx->max_batch : RDFE_MAX_BATCH);
         return RDFE_ERR_INVALID;
     }
     out->n = n;
@@ -308,17 +308,21 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     ctx->raw_slot = align_up(ctx->raw_pitch * cfg->height, 256);
     CK(cudaMalloc(&ctx->raw, ctx->raw_slot * cfg->num_slots));
     CK(cudaMalloc(&ctx->lut, (size_t)RDFE_MAX_BATCH * kMaxTiles * kMaxTiles * 256));
+    // a batch never holds more images than there are slots: the large per-image scratch is sized by that, not by
+    // RDFE_MAX_BATCH (a single-stream plugin context with 4 slots needs 1/32 of the candidate memory)
+    ctx->max_batch = cfg->num_slots < RDFE_MAX_BATCH ? cfg->num_slots : RDFE_MAX_BATCH;
+    const size_t mb = (size_t)ctx->max_batch;
     ctx->det.cand_cap = (unsigned)((size_t)cfg->width * cfg->height / 2);
-    CK(cudaMalloc(&ctx->det.cand, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
-    CK(cudaMalloc(&ctx->det.cand2, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det.cand, mb * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det.cand2, mb * ctx->det.cand_cap * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->det.cand_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.flag_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det.overflow, sizeof(unsigned)));
     CK(cudaMemset(ctx->det.overflow, 0, sizeof(unsigned)));
     ctx->det2 = ctx->det;
-    CK(cudaMalloc(&ctx->det2.cand, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
-    CK(cudaMalloc(&ctx->det2.cand2, (size_t)RDFE_MAX_BATCH * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det2.cand, mb * ctx->det.cand_cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->det2.cand2, mb * ctx->det.cand_cap * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->det2.cand_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det2.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det2.flag_count, RDFE_MAX_BATCH * sizeof(unsigned)));
@@ -374,6 +378,7 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMallocHost(&ctx->h_overflow, sizeof(unsigned)));
     *ctx->h_overflow = 0u;
     ctx->host_sync = true;
+    ctx->compact_tracked = true;
     ctx->slot_new_step = (long long *)malloc((size_t)cfg->num_slots * sizeof(long long));
     for (int i = 0; i < cfg->num_slots; ++i) ctx->slot_new_step[i] = -16;
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -452,6 +457,13 @@ void rdfe_destroy(rdfe_ctx *ctx) {
 
 int rdfe_num_levels(const rdfe_ctx *ctx) { return ctx ? ctx->pyr.nlevels : RDFE_ERR_INVALID; }
 
+// det.overflow bits: 1 = corner-candidate buffer full (harris), 2 = keypoint list cut at `stride` (poisson append)
+static int report_overflow(rdfe_ctx *ctx, unsigned bits) {
+    if (bits & 1u) set_error("corner-candidate buffer overflow (more than %u local maxima in one image)", ctx->det.cand_cap);
+    else set_error("keypoint list truncated: existing + new keypoints exceed `stride` (the reference's vector is unbounded; pass a larger stride)");
+    return RDFE_ERR_OVERFLOW;
+}
+
 int rdfe_level_size(const rdfe_ctx *ctx, int level, int *width, int *height) {
     if (!ctx || level < 0 || level >= ctx->pyr.nlevels) { set_error("rdfe_level_size: bad level %d", level); return RDFE_ERR_INVALID; }
     if (width) *width = ctx->pyr.lv[level].w;
@@ -466,8 +478,7 @@ int rdfe_sync(rdfe_ctx *ctx) {
     RDFE_CUDA_OK(cudaMemcpy(&ovf, ctx->det.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
     if (ovf) {
         cudaMemset(ctx->det.overflow, 0, sizeof(unsigned));
-        set_error("corner-candidate buffer overflow (more than %u local maxima in one image)", ctx->det.cand_cap);
-        return RDFE_ERR_OVERFLOW;
+        return report_overflow(ctx, ovf);
     }
     return RDFE_OK;
 }
@@ -576,7 +587,7 @@ int rdfe_detect_batch_dev(rdfe_ctx *ctx, const int *slots, int n, const rdfe_det
         ctx->pf_valid = false;
         RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->pf_done, 0));
         return check_launch(ctx, launch_poisson_append(ctx, n, *p, ctx->pf_gftt_xy, ctx->pf_gftt_counts, dev_keypoints_xy,
-                                                       dev_counts, stride), "poisson");
+                                                       dev_counts, stride, nullptr), "poisson");
     }
     rc = check_launch(ctx, launch_harris_candidates(ctx, sl, *p, nullptr), "harris");
     if (rc) return rc;
@@ -608,6 +619,12 @@ int rdfe_detect_prefetch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_dete
     ctx->pf_n = n;
     for (int i = 0; i < n; ++i) ctx->pf_slots[i] = slots[i];
     ctx->pf_params = *p;
+    return RDFE_OK;
+}
+
+int rdfe_set_step_compaction(rdfe_ctx *ctx, int on) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    ctx->compact_tracked = on != 0;
     return RDFE_OK;
 }
 
@@ -643,8 +660,7 @@ int rdfe_detect_batch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // everything this call launched is ordered on the main stream
     if (*ctx->h_overflow) {
         cudaMemsetAsync(ctx->det.overflow, 0, sizeof(unsigned), ctx->stream);
-        set_error("corner-candidate buffer overflow (more than %u local maxima in one image)", ctx->det.cand_cap);
-        return RDFE_ERR_OVERFLOW;
+        return report_overflow(ctx, *ctx->h_overflow);
     }
     return RDFE_OK;
 }
@@ -800,7 +816,8 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         cudaStreamWaitEvent(po, ctx->ev_lk_done[par], 0);
         cudaStreamWaitEvent(po, evj, 0);
         ctx->ls = po;
-        rc = check_launch(ctx, launch_poisson_append(ctx, n, *dp, gxy, gcn, dev_next_xy, dev_kp_counts, stride), "poisson");
+        rc = check_launch(ctx, launch_poisson_append(ctx, n, *dp, gxy, gcn, dev_next_xy, dev_kp_counts, stride,
+                                                     (prev_slots && ctx->compact_tracked) ? dev_status : nullptr), "poisson");
         restore_p();
         if (rc) return rc;
         RDFE_CUDA_OK(cudaEventRecord(ctx->ev_step_done[par], po));
@@ -850,7 +867,8 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         if (rc) return rc;
     }
     if (ov) RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, evj, 0));
-    rc = check_launch(ctx, launch_poisson_append(ctx, n, *dp, gxy, gcn, dev_next_xy, dev_kp_counts, stride), "poisson");
+    rc = check_launch(ctx, launch_poisson_append(ctx, n, *dp, gxy, gcn, dev_next_xy, dev_kp_counts, stride,
+                                                     (prev_slots && ctx->compact_tracked) ? dev_status : nullptr), "poisson");
     if (rc) return rc;
     RDFE_CUDA_OK(cudaEventRecord(ctx->ev_step_done[par], ctx->stream));
     memset(ctx->last_step_slots, 0, (size_t)ctx->cfg.num_slots);
@@ -969,6 +987,24 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
     return RDFE_OK;
 }
 
+// Measurement aid: exactly the frame upload of rdfe_frontend_step_submit (same staging, same copy stream, same
+// one-2-D-copy path), no kernels.  bench.py times it alone to show what the host side of a box can deliver.
+int rdfe_upload_only(rdfe_ctx *ctx, const int *new_slots, int n, const uint8_t *const *images, size_t pitch, int sync) {
+    if (!ctx || !new_slots || !images || n < 1 || n > ctx->max_batch) { set_error("rdfe_upload_only: bad argument"); return RDFE_ERR_INVALID; }
+    if (pitch < (size_t)ctx->cfg.width * ctx->in_channels) { set_error("rdfe_upload_only: pitch < width * channels"); return RDFE_ERR_INVALID; }
+    for (int i = 0; i < n; ++i)
+        if (new_slots[i] < 0 || new_slots[i] >= ctx->cfg.num_slots || !ctx->slot_used[new_slots[i]] || !images[i]) {
+            set_error("rdfe_upload_only: bad slot or image at index %d", i);
+            return RDFE_ERR_INVALID;
+        }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    std::vector<const uint8_t *> dptr(n);
+    const int rc = upload_frames(ctx, ctx->copy_stream, new_slots, n, images, pitch, dptr);
+    if (rc) return rc;
+    if (sync) RDFE_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));
+    return RDFE_OK;
+}
+
 int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy, int *kp_counts, char *status) {
     if (!ctx) return RDFE_ERR_INVALID;
     const int p = ticket & 1;
@@ -985,8 +1021,7 @@ int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy, int *kp_
     ctx->pl_busy[p] = 0;
     if (ovf) {
         cudaMemsetAsync(ctx->det.overflow, 0, sizeof(unsigned), ctx->stream);
-        set_error("corner-candidate buffer overflow (more than %u local maxima in one image)", ctx->det.cand_cap);
-        return RDFE_ERR_OVERFLOW;
+        return report_overflow(ctx, ovf);
     }
     return RDFE_OK;
 }

@@ -371,13 +371,12 @@ int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_s
     const size_t smem = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint32_t) + (size_t)((cp.W + 3) & ~3) * 8;
     const size_t smem_fast = (size_t)(cp.tiles_x + 1) * 256 * sizeof(uint2) + (size_t)cp.W * 12;
     if (src_vec4 && cp.W % 4 == 0 && smem_fast <= 100 * 1024) {
-        static size_t s_attr = 0;
-        if (smem_fast > 48 * 1024 && smem_fast > s_attr) {
+        if (smem_fast > 48 * 1024 && smem_fast > ctx->smem_optin[2]) {      // per-device attribute: remembered per context
             if (cudaFuncSetAttribute(clahe_apply_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast) != cudaSuccess) {
                 set_error("clahe: cudaFuncSetAttribute(%zu) failed", smem_fast);
                 return RDFE_ERR_CUDA;
             }
-            s_attr = smem_fast;
+            ctx->smem_optin[2] = smem_fast;
         }
         RDFE_LAUNCH(ctx, K_CLAHE_APPLY, (clahe_apply_fast_kernel<<<g2, 256, smem_fast, ctx->ls>>>(d_src, src_pitch, cp, bands, ctx->lut,
                                                                                                    ctx->pyr, slots)));

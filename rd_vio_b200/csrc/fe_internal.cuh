@@ -192,6 +192,9 @@ struct rdfe_ctx {
     cudaEvent_t pf_done;
     float *pf_gftt_xy, *pf_gftt_resp;
     int *pf_gftt_counts;
+    int max_batch;                // min(num_slots, RDFE_MAX_BATCH): images per batched call on this context
+    bool compact_tracked;         // fused step: only status != 0 points are carried into detect (frame.cpp:160-170); default on
+    size_t smem_optin[4];         // per-context (= per-device) dynamic shared memory already granted: select, poisson, clahe, spare
     bool host_sync;               // host-pointer preprocess waits for completion (default) or returns after the upload
     unsigned *h_overflow;         // pinned copy of det.overflow for the host-pointer detect
     rdfe::DetectScratch det2;     // candidate buffers of odd steps (cand, cand2, count, max; overflow flag shared)
@@ -291,7 +294,8 @@ int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params
 int launch_gftt_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, float *d_gftt_xy,
                        float *d_gftt_resp, int *d_gftt_counts);
 int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, const float *d_gftt_xy,
-                          const int *d_gftt_counts, double *d_xy, int *d_counts, int stride);
+                          const int *d_gftt_counts, double *d_xy, int *d_counts, int stride,
+                          const char *d_lk_status /* optional: keep only status != 0 presets (frame.cpp:160-170) */);
 int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t src_pitch, int src_vec4, uint8_t *const *d_dst,
                      size_t dst_pitch);
 int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const rdfe_track_params &p,

@@ -421,7 +421,8 @@ constexpr int PO_THREADS = 512;
 
 __global__ void __launch_bounds__(PO_THREADS)
 poisson_append_kernel(SelectParams sp, const float *__restrict__ gftt_xy, const int *__restrict__ gftt_counts,
-                      double *__restrict__ kp_xy, int *__restrict__ kp_counts) {
+                      double *__restrict__ kp_xy, int *__restrict__ kp_counts, const char *__restrict__ lk_status,
+                      unsigned *__restrict__ truncated) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *pxs = reinterpret_cast<double *>(smem_raw);                                     // [stride] preset x
     double *pys = pxs + sp.stride;                                                          // [stride] preset y
@@ -439,16 +440,41 @@ poisson_append_kernel(SelectParams sp, const float *__restrict__ gftt_xy, const 
     const int b = blockIdx.x;
     const int na = min(gftt_counts[b], sp.cap_k);
     double *pts = kp_xy + (size_t)b * sp.stride * 2;
-    const int ne = min(kp_counts[b], sp.stride);
+    int ne = min(kp_counts[b], sp.stride);
     const double radius = sp.kp_radius, r2 = radius * radius;
     const double gsz = radius / sqrt(2.0);
     const int span = (int)ceil(sqrt(2.0));
     // ---- load presets and candidates, compute their grid cells once (float64 division: reference semantics)
     for (int i = tid; i < ne; i += PO_THREADS) {
-        const double x = pts[2 * i], y = pts[2 * i + 1];
-        pxs[i] = x; pys[i] = y;
-        pcx[i] = (int)floor(x / gsz);
-        pcy[i] = (int)floor(y / gsz);
+        pxs[i] = pts[2 * i]; pys[i] = pts[2 * i + 1];
+        pflag[i] = lk_status ? (lk_status[(size_t)b * sp.stride + i] != 0) : 1;
+    }
+    if (lk_status) {
+        // Frame::track_keypoints appends only the status != 0 points to the next frame, in order (frame.cpp:160-170);
+        // those are the existing keypoints detect sees.  Stable in-place compaction by warp 0 (writes never pass reads).
+        __shared__ int s_ne;
+        __syncthreads();
+        if (warp == 0) {
+            int w = 0;
+            for (int base = 0; base < ne; base += 32) {
+                const int i = base + lane;
+                const bool keep = i < ne && pflag[i];
+                const double x = i < ne ? pxs[i] : 0.0, y = i < ne ? pys[i] : 0.0;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int pos = w + __popc(m & ((1u << lane) - 1u));
+                __syncwarp();
+                if (keep) { pxs[pos] = x; pys[pos] = y; }
+                w += __popc(m);
+            }
+            if (lane == 0) s_ne = w;
+        }
+        __syncthreads();
+        ne = s_ne;
+        for (int i = tid; i < ne; i += PO_THREADS) { pts[2 * i] = pxs[i]; pts[2 * i + 1] = pys[i]; }
+    }
+    for (int i = tid; i < ne; i += PO_THREADS) {
+        pcx[i] = (int)floor(pxs[i] / gsz);
+        pcy[i] = (int)floor(pys[i] / gsz);
         pflag[i] = 1;
     }
     for (int c = tid; c < na; c += PO_THREADS) {
@@ -496,6 +522,7 @@ poisson_append_kernel(SelectParams sp, const float *__restrict__ gftt_xy, const 
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             const int pos = nout + __popc(m & ((1u << lane) - 1u));
             if (keep && pos < sp.stride) { pts[2 * pos] = cx; pts[2 * pos + 1] = cy; }
+            if (nout + __popc(m) > sp.stride && lane == 0) atomicOr(truncated, 2u);   // the reference's vector is unbounded
             nout = min(nout + __popc(m), sp.stride);
         }
     } else {
@@ -518,9 +545,11 @@ poisson_append_kernel(SelectParams sp, const float *__restrict__ gftt_xy, const 
             ++nins;
             __syncwarp();
             const bool out_of_border = cx < sp.border || cy < sp.border || cx >= sp.W - sp.border || cy >= sp.H - sp.border;
-            if (!out_of_border && nout < sp.stride) {
-                if (lane == 0) { pts[2 * nout] = cx; pts[2 * nout + 1] = cy; }
-                ++nout;
+            if (!out_of_border) {
+                if (nout < sp.stride) {
+                    if (lane == 0) { pts[2 * nout] = cx; pts[2 * nout + 1] = cy; }
+                    ++nout;
+                } else if (lane == 0) atomicOr(truncated, 2u);
             }
         }
     }
@@ -558,33 +587,32 @@ int launch_gftt_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_p
                   p.max_points, sp.gw, sp.gh);
         return RDFE_ERR_UNSUPPORTED;
     }
-    static size_t s_attr = 0;
-    if (smem > 48 * 1024 && smem > s_attr) {
+    // the opt-in is a per-device attribute: remembered per context (a context is bound to one device)
+    if (smem > 48 * 1024 && smem > ctx->smem_optin[0]) {
         if (cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             set_error("select: cudaFuncSetAttribute(%zu) failed", smem);
             return RDFE_ERR_CUDA;
         }
-        s_attr = smem;
+        ctx->smem_optin[0] = smem;
     }
     RDFE_LAUNCH(ctx, K_SELECT, (select_kernel<<<n, SEL_THREADS, smem, ctx->ls>>>(ctx->det, sp, ctx->pyr, slots, d_gftt_xy, d_gftt_resp, d_gftt_counts)));
     return 1;
 }
 
 int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, const float *d_gftt_xy,
-                          const int *d_gftt_counts, double *d_xy, int *d_counts, int stride) {
+                          const int *d_gftt_counts, double *d_xy, int *d_counts, int stride, const char *d_lk_status) {
     SelectParams sp;
     fill_select_params(ctx, p, stride, sp);
     const size_t smem = (size_t)sp.cap_k * 21 + (size_t)stride * 25 + 64;
     if (smem > 200 * 1024) { set_error("poisson: shared memory need %zu B too large", smem); return RDFE_ERR_UNSUPPORTED; }
-    static size_t s_attr = 0;
-    if (smem > 48 * 1024 && smem > s_attr) {
+    if (smem > 48 * 1024 && smem > ctx->smem_optin[1]) {
         if (cudaFuncSetAttribute(poisson_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             set_error("poisson: cudaFuncSetAttribute(%zu) failed", smem);
             return RDFE_ERR_CUDA;
         }
-        s_attr = smem;
+        ctx->smem_optin[1] = smem;
     }
-    RDFE_LAUNCH(ctx, K_POISSON, (poisson_append_kernel<<<n, PO_THREADS, smem, ctx->ls>>>(sp, d_gftt_xy, d_gftt_counts, d_xy, d_counts)));
+    RDFE_LAUNCH(ctx, K_POISSON, (poisson_append_kernel<<<n, PO_THREADS, smem, ctx->ls>>>(sp, d_gftt_xy, d_gftt_counts, d_xy, d_counts, d_lk_status, ctx->det.overflow)));
     return 1;
 }
 
@@ -596,7 +624,7 @@ int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params
     int rc = launch_gftt_select(ctx, slots, p, gxy, gre, gcn);
     if (rc < 0) return rc;
     if (!d_xy) return 1;
-    rc = launch_poisson_append(ctx, slots.n, p, gxy, gcn, d_xy, d_counts, stride);
+    rc = launch_poisson_append(ctx, slots.n, p, gxy, gcn, d_xy, d_counts, stride, nullptr);
     return rc < 0 ? rc : 2;
 }
 

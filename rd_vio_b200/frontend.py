@@ -124,7 +124,8 @@ class FrontEnd:
         ex = [np.asarray(e, np.float64).reshape(-1, 2) for e in existing]
         if stride is None:
             stride = max(len(e) for e in ex) + max_points
-        stride = min(stride, self.max_points)
+        if stride > self.max_points:       # the reference's vector is unbounded: never clamp silently
+            raise ValueError(f"existing + max_points = {stride} keypoints exceed the context capacity {self.max_points}")
         xy = np.zeros((n, stride, 2), np.float64)
         counts = np.zeros(n, np.int32)
         for i, e in enumerate(ex):

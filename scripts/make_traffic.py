@@ -1,6 +1,7 @@
-"""Per-kernel DRAM bytes per launch from an ncu launch list (long CSV format:
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv):
-python scripts/make_traffic.py profiles/r1_launches_final.csv profiles/r1_traffic.json"""
+"""Per-kernel DRAM bytes, warp instructions and shared-memory wavefronts per launch from an ncu launch list (long CSV:
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,
+l1tex__data_pipe_lsu_wavefronts_mem_shared.sum --clock-control none --csv):
+python scripts/make_traffic.py profiles/r2_launches_final.csv profiles/r2_traffic.json"""
 import collections, csv, json, sys
 
 src, dst = sys.argv[1], sys.argv[2]
@@ -11,18 +12,22 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us"
 acc = collections.OrderedDict()
 for r in rows[1:]:
     name = r[ik].split("(")[0].replace("rdfe::", "").replace("void ", "").strip()
-    a = acc.setdefault(name, {"ids": set(), "rd": 0.0, "wr": 0.0, "us": 0.0})
+    a = acc.setdefault(name, {"ids": set(), "rd": 0.0, "wr": 0.0, "us": 0.0, "inst": 0.0, "smem": 0.0})
     a["ids"].add(r[iid])
     v = float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
     if r[im] == "dram__bytes_read.sum": a["rd"] += v
     elif r[im] == "dram__bytes_write.sum": a["wr"] += v
     elif r[im] == "gpu__time_duration.sum": a["us"] += v
-out = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none (%s), "
+    elif r[im] == "smsp__inst_executed.sum": a["inst"] += v
+    elif r[im] == "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": a["smem"] += v
+out = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,"
+                 "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum --clock-control none (%s), "
                  "bench.py --steps 4 --warmup 3, 64 streams 752x480" % src, "kernels": {}}
 for name, a in acc.items():
     n = len(a["ids"])
     out["kernels"][name] = {"launches": n, "dram_read_bytes_per_launch": a["rd"] / n, "dram_write_bytes_per_launch": a["wr"] / n,
-                            "mean_us_under_ncu": a["us"] / n}
+                            "mean_us_under_ncu": a["us"] / n, "warp_inst_per_launch": a["inst"] / n,
+                            "smem_wavefronts_per_launch": a["smem"] / n}
 json.dump(out, open(dst, "w"), indent=1)
 # shares of the serialised step: only the steady-state steps (from the first step that tracks, i.e. launches LK)
 first_lk = min((int(i) for n, a in acc.items() if n.startswith("lk_track") for i in a["ids"]), default=0) - 9

@@ -1,5 +1,5 @@
 """Test helper: the reference's Image plugin interface on top of the CPU oracle (TEST INFRASTRUCTURE ONLY), so that
-rd_vio_b200.frame.FeatureTracker can be replayed once on the oracle and once on the GPU plugin."""
+oracle.frame_host.FeatureTracker can be replayed once on the oracle and once on the GPU plugin."""
 import numpy as np
 
 
@@ -36,7 +36,7 @@ class OracleImage:
 
 def replay(stream, n_frames, make_image, start=0):
     """FeatureTracker::run over frames start..start+n_frames-1 of a synthetic stream; per frame (pixels, track ids)."""
-    from rd_vio_b200.frame import FeatureTracker, Frame, q_from_matrix
+    from oracle.frame_host import FeatureTracker, Frame, q_from_matrix
     ft, out = FeatureTracker(), []
     for i in range(n_frames):
         k = start + i

@@ -1,9 +1,9 @@
-"""CPU: the host-side mirror of the plugin's callers (rd_vio_b200/frame.py) against the
+"""CPU: the host-side mirror of the plugin's callers (oracle/frame_host.py) against the
 oracle's independent restatements and against properties the reference's formulas guarantee."""
 import numpy as np
 import pytest
 
-from rd_vio_b200 import frame as F
+from oracle import frame_host as F
 
 
 def test_apply_remove_k_round_trip_and_formula(stream0):

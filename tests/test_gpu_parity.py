@@ -274,10 +274,8 @@ def test_fused_step_equals_separate_calls(orc, stream0, frames0):
         fe.preprocess(list(new), frames0[1:n + 1])
         nxt, st = fe.track(list(prev), list(new), kps, preds)
         want = []
-        for i in range(n):
-            ex = preds[i].copy()
-            ex[st[i] != 0] = nxt[i][st[i] != 0]
-            want.append(fe.detect([int(new[i])], [ex], 150, 20.0, stride=stride)[0])
+        for i in range(n):      # Frame::track_keypoints carries only the status != 0 points into detect (frame.cpp:160-170)
+            want.append(fe.detect([int(new[i])], [nxt[i][st[i] != 0]], 150, 20.0, stride=stride)[0])
         # fused device call
         curr = torch.zeros((n, stride, 2), dtype=torch.float64)
         work = torch.zeros((n, stride, 2), dtype=torch.float64)
@@ -324,10 +322,8 @@ def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
             fe.preprocess(list(b), frames0[stp + 1:stp + 1 + n])
             nxt, st = fe.track(list(a), list(b), carried, None)
             merged = []
-            for i in range(n):
-                ex = carried[i].copy()
-                ex[st[i] != 0] = nxt[i][st[i] != 0]
-                merged.append(fe.detect([int(b[i])], [ex], 150, 20.0, stride=stride)[0])
+            for i in range(n):  # only tracked points are carried (frame.cpp:160-170)
+                merged.append(fe.detect([int(b[i])], [nxt[i][st[i] != 0]], 150, 20.0, stride=stride)[0])
             want.append((merged, st))
             carried = [m[:stride] for m in merged]
         # pipelined: submit step 0 and step 1 back to back (step 1's input = step 0's expected output), then wait

@@ -131,7 +131,7 @@ def test_cpp_plugin_replay_200_frames(tmp_path):
 
 
 def test_feature_tracker_replay_with_imu_prediction():
-    """the plugin driven by the reference's callers (rd_vio_b200/frame.py: pixels from unit
+    """the plugin driven by the reference's callers (oracle/frame_host.py: pixels from unit
     bearings through K, predictions = bearings rotated by the gyro increment, track-length-ordered Poisson filter,
     detect on what survived), 40 frames, GPU plugin against the same loop on the CPU oracle: identical track ids
     and keypoint counts in every frame, positions within 0.01 px."""
