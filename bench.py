@@ -381,18 +381,20 @@ def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e
         h2d = S * H * W + 2 * S * stride * 16 + 2 * S * 4
         d2h = S * stride * 16 + S * 4 + S * stride + 4
         e_steps = max(10, min(steps, 200))
-        tk = submit(t); t += 1
-        for _ in range(3):                       # warm the pipeline
-            tk2 = submit(t); t += 1
-            wait(tk); tk = tk2
-        wait(tk)
+        def run_pipelined(nsteps, tt):       # up to three steps in flight (rdfe_frontend_step_submit's pipeline depth)
+            pending = []
+            for _ in range(nsteps):
+                pending.append(submit(tt)); tt += 1
+                if len(pending) == 3:
+                    wait(pending.pop(0))
+            while pending:
+                wait(pending.pop(0))
+            return tt
+
+        t = run_pipelined(6, t)                  # warm the pipeline
         barrier()
         w0 = time.perf_counter()
-        tk = submit(t); t += 1
-        for _ in range(e_steps - 1):
-            tk2 = submit(t); t += 1
-            wait(tk); tk = tk2
-        wait(tk)
+        t = run_pipelined(e_steps, t)
         barrier()
         sec = time.perf_counter() - w0
         e_value, sec_max_ms = PAR.aggregate_throughput(S * e_steps, sec * 1e3, dist, torch.device("cuda", local))
@@ -416,7 +418,7 @@ def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e
                             "e2e_over_copy_only": e_value / c_value if c_value > 0 else None,
                             "how": "rdfe_upload_only: the frame uploads of the same steps alone (same pinned buffers, same "
                                    "staging, copy stream and one strided 2-D copy per step), no kernels, all ranks at once"},
-               "how": "rdfe_frontend_step_submit/_wait (C ABI, pinned HOST buffers, two steps in flight): every step "
+               "how": "rdfe_frontend_step_submit/_wait (C ABI, pinned HOST buffers, three steps in flight): every step "
                       f"copies its {S} frames + carried keypoints + predictions H2D and its tracked/detected keypoints, "
                       "counts and status D2H; wall clock bracketed by barrier+synchronize, max over ranks"}
 

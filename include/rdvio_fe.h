@@ -207,10 +207,10 @@ RDFE_API int rdfe_set_pipelining(rdfe_ctx *ctx, int on);
  * suppressing new corners -- the round-1 behaviour, kept for A/B measurements. */
 RDFE_API int rdfe_set_step_compaction(rdfe_ctx *ctx, int on);
 
-/* Host-buffer form of the same step, pipelined two deep: submit() uploads the frames and keypoints on a copy
- * stream and enqueues the step; wait() blocks until that step's results are on the host and copies them out.
- * submit(t+1) may precede wait(t) so that the upload of the next frames overlaps the kernels of the current
- * step.  next_xy [n][stride][2]: positions of the carried keypoints (prediction where tracking failed) followed
+/* Host-buffer form of the same step, pipelined up to three deep: submit() uploads the frames and keypoints on a
+ * copy stream and enqueues the step; wait() blocks until that step's results are on the host and copies them out.
+ * submit(t+1) and submit(t+2) may precede wait(t) so that the uploads of the next frames overlap the kernels of the
+ * current step and the copy engine never idles while the host collects results (a fourth un-waited submit is refused).  next_xy [n][stride][2]: positions of the carried keypoints (prediction where tracking failed) followed
  * by the newly detected corners (with step compaction, the default: only the tracked ones, in order, followed by
  * the new corners), kp_counts[i] entries; status [n][stride] in the input's indexing.  pred_xy may be NULL (seed with
  * curr_xy); prev_slots may be NULL (no tracking, counts[i] existing keypoints are taken from curr_xy = NULL -> 0). */

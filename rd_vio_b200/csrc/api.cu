@@ -383,7 +383,11 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     for (int i = 0; i < cfg->num_slots; ++i) ctx->slot_new_step[i] = -16;
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_clahe_done, cudaEventDisableTiming));
-    for (int p = 0; p < 2; ++p) {
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_clahe_ring[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_copy_fence, cudaEventDisableTiming));
+    ctx->slot_clahe_step = (long long *)malloc((size_t)cfg->num_slots * sizeof(long long));
+    for (int i = 0; i < cfg->num_slots; ++i) ctx->slot_clahe_step[i] = -1;
+    for (int p = 0; p < kPipeDepth; ++p) {
         CK(cudaEventCreateWithFlags(&ctx->ev_upload[p], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_done[p], cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->pl_curr[p], npts * 2 * sizeof(double)));
@@ -437,7 +441,10 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     cudaFree(ctx->lut2); cudaFree(ctx->d_srcptrs2); cudaFree(ctx->d_gftt_xy2); cudaFree(ctx->d_gftt_resp2); cudaFree(ctx->d_gftt_counts2);
     free(ctx->last_step_slots);
     if (ctx->ev_clahe_done) cudaEventDestroy(ctx->ev_clahe_done);
-    for (int p = 0; p < 2; ++p) {
+    for (int i = 0; i < 4; ++i) if (ctx->ev_clahe_ring[i]) cudaEventDestroy(ctx->ev_clahe_ring[i]);
+    if (ctx->ev_copy_fence) cudaEventDestroy(ctx->ev_copy_fence);
+    free(ctx->slot_clahe_step);
+    for (int p = 0; p < kPipeDepth; ++p) {
         if (ctx->ev_upload[p]) cudaEventDestroy(ctx->ev_upload[p]);
         if (ctx->ev_done[p]) cudaEventDestroy(ctx->ev_done[p]);
         cudaFree(ctx->pl_curr[p]); cudaFree(ctx->pl_next[p]); cudaFree(ctx->pl_counts[p]); cudaFree(ctx->pl_kcounts[p]);
@@ -541,6 +548,7 @@ int rdfe_preprocess_batch(rdfe_ctx *ctx, const int *slots, int n, const uint8_t 
     std::vector<const uint8_t *> dptr(n);
     for (int i = 0; i < n; ++i)
         if (!images[i]) { set_error("rdfe_preprocess_batch: image %d is null", i); return RDFE_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) ctx->slot_clahe_step[slots[i]] = -1;      // raw staging now ordered on the context stream
     rc = upload_frames(ctx, ctx->stream, slots, n, images, pitch, dptr);
     if (rc) return rc;
     rc = rdfe_preprocess_batch_dev(ctx, slots, n, dptr.data(), ctx->raw_pitch, clip_limit, tiles_x, tiles_y);
@@ -782,6 +790,8 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), d_src, spitch, vec4, cp), "clahe");
         if (rc) { restore_p(); return rc; }
         cudaEventRecord(ctx->ev_clahe_done, ps);
+        cudaEventRecord(ctx->ev_clahe_ring[ctx->step_index & 3], ps);
+        for (int i = 0; i < n; ++i) ctx->slot_clahe_step[new_slots[i]] = (long long)ctx->step_index;
         cudaEventRecord(ctx->ev_apply_done, ps);
         rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
         if (rc) { restore_p(); return rc; }
@@ -845,6 +855,8 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
     rc = check_launch(ctx, launch_clahe(ctx, sl_copy(sn), d_src, spitch, vec4, cp), "clahe");
     if (rc) { restore(); return rc; }
     cudaEventRecord(ctx->ev_clahe_done, ps);
+    cudaEventRecord(ctx->ev_clahe_ring[ctx->step_index & 3], ps);
+    for (int i = 0; i < n; ++i) ctx->slot_clahe_step[new_slots[i]] = (long long)ctx->step_index;
     cudaEventRecord(ctx->ev_apply_done, ps);
     // ---- detection branch (Harris needs only level 0): auxiliary stream
     cudaStream_t axs = ctx->aux_stream;
@@ -936,8 +948,8 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
     }
     if (prev_slots && (!tp || !curr_xy)) { set_error("rdfe_frontend_step_submit: tracking needs tp and curr_xy"); return RDFE_ERR_INVALID; }
     if (pitch < (size_t)ctx->cfg.width * ctx->in_channels) { set_error("rdfe_frontend_step_submit: pitch < width * channels"); return RDFE_ERR_INVALID; }
-    const int p = (int)(ctx->pl_ticket & 1);
-    if (ctx->pl_busy[p]) { set_error("rdfe_frontend_step_submit: stage %d still holds un-waited results (at most 2 steps in flight)", p); return RDFE_ERR_INVALID; }
+    const int p = (int)(ctx->pl_ticket % kPipeDepth);
+    if (ctx->pl_busy[p]) { set_error("rdfe_frontend_step_submit: stage %d still holds un-waited results (at most 3 steps in flight)", p); return RDFE_ERR_INVALID; }
     for (int i = 0; i < n; ++i) {
         if (new_slots[i] < 0 || new_slots[i] >= ctx->cfg.num_slots || !ctx->slot_used[new_slots[i]] || !images[i]) {
             set_error("rdfe_frontend_step_submit: bad slot or image at index %d", i);
@@ -948,7 +960,28 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
     const size_t xyb = (size_t)n * stride * 2 * sizeof(double);
     // ---- copy stream: frames into the upload staging of the new slots, keypoints into stage p
-    RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_clahe_done, 0));     // last reader of the raw staging
+    // The upload overwrites the raw staging of the NEW slots: it must wait for the last CLAHE that read them.  With
+    // slot sets in rotation that is the CLAHE of an older step (s-3 for three sets), not the one just enqueued, so
+    // the upload of step s+1 runs while step s is still waiting for its own frames' kernels.
+    {
+        long long last = -1;
+        bool unknown = false;
+        for (int i = 0; i < n; ++i) {
+            const long long v = ctx->slot_clahe_step[new_slots[i]];
+            if (v < 0) unknown = true;
+            if (v > last) last = v;
+        }
+        const long long cur = (long long)ctx->step_index;
+        if (unknown || cur == 0) {                         // conservative: everything enqueued so far
+            RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_clahe_done, 0));
+            RDFE_CUDA_OK(cudaEventRecord(ctx->ev_copy_fence, ctx->stream));
+            RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_fence, 0));
+        }
+        else {
+            if (last < cur - 4) last = cur - 4;            // older entries were re-recorded; CLAHEs complete in step order
+            RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_clahe_ring[last & 3], 0));
+        }
+    }
     RDFE_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[p], 0));        // stage buffers free again
     std::vector<const uint8_t *> dptr(n);
     {
@@ -982,7 +1015,7 @@ int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *n
     RDFE_CUDA_OK(cudaMemcpyAsync(hs + xyb + n * sizeof(int) + (size_t)n * stride, ctx->det.overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     RDFE_CUDA_OK(cudaEventRecord(ctx->ev_done[p], ctx->stream));
     ctx->pl_n[p] = n; ctx->pl_stride[p] = stride; ctx->pl_busy[p] = prev_slots ? 2 : 1;
-    *ticket = (int)(ctx->pl_ticket & 0x7fffffff);
+    *ticket = (int)(ctx->pl_ticket % (3 * (1LL << 28)));      // stays a multiple-of-3-periodic non-negative int
     ctx->pl_ticket++;
     return RDFE_OK;
 }
@@ -1007,7 +1040,7 @@ int rdfe_upload_only(rdfe_ctx *ctx, const int *new_slots, int n, const uint8_t *
 
 int rdfe_frontend_step_wait(rdfe_ctx *ctx, int ticket, double *next_xy, int *kp_counts, char *status) {
     if (!ctx) return RDFE_ERR_INVALID;
-    const int p = ticket & 1;
+    const int p = ticket % kPipeDepth;
     if (!ctx->pl_busy[p]) { set_error("rdfe_frontend_step_wait: ticket %d has no pending step", ticket); return RDFE_ERR_INVALID; }
     RDFE_CUDA_OK(cudaEventSynchronize(ctx->ev_done[p]));
     const int n = ctx->pl_n[p], stride = ctx->pl_stride[p];

@@ -12,6 +12,10 @@
 #include "../../include/rdvio_fe.h"
 
 namespace rdfe {
+// steps the host-buffer pipeline (rdfe_frontend_step_submit/_wait) may hold in flight: with three, the upload of
+// step s+2 is already queued while step s computes, so the copy engine never waits for the host to come back
+constexpr int kPipeDepth = 3;
+
 
 constexpr int kHaloX = 32;          // left halo columns of an image plane (>= win, keeps interior 32-B aligned)
 constexpr int kMaxTiles = 16;       // CLAHE tiles per axis
@@ -219,13 +223,16 @@ struct rdfe_ctx {
     // pipelined host-buffer step (rdfe_frontend_step_submit / _wait): two stages
     cudaStream_t copy_stream;     // H2D of the next step's frames overlaps the current step's kernels
     cudaEvent_t ev_clahe_done;    // raw upload staging may be overwritten after this
-    cudaEvent_t ev_upload[2], ev_done[2];
-    double *pl_curr[2], *pl_next[2];      // device [RDFE_MAX_BATCH][max_points][2]
-    int *pl_counts[2], *pl_kcounts[2];
-    char *pl_status[2];
-    unsigned *pl_ovf[2];
-    uint8_t *pl_host[2];          // pinned result staging: next_xy | kcounts | status | overflow
-    int pl_n[2], pl_stride[2], pl_busy[2];
+    cudaEvent_t ev_copy_fence;    // tail of the context stream, for uploads into slots last preprocessed by the separate calls
+    cudaEvent_t ev_clahe_ring[4]; // CLAHE of fused step s done: ring entry s & 3
+    long long *slot_clahe_step;   // [num_slots] fused step whose CLAHE last read the slot's raw staging (-1: not by a fused step)
+    cudaEvent_t ev_upload[rdfe::kPipeDepth], ev_done[rdfe::kPipeDepth];
+    double *pl_curr[rdfe::kPipeDepth], *pl_next[rdfe::kPipeDepth];      // device [RDFE_MAX_BATCH][max_points][2]
+    int *pl_counts[rdfe::kPipeDepth], *pl_kcounts[rdfe::kPipeDepth];
+    char *pl_status[rdfe::kPipeDepth];
+    unsigned *pl_ovf[rdfe::kPipeDepth];
+    uint8_t *pl_host[rdfe::kPipeDepth];   // pinned result staging: next_xy | kcounts | status | overflow
+    int pl_n[rdfe::kPipeDepth], pl_stride[rdfe::kPipeDepth], pl_busy[rdfe::kPipeDepth];
     int64_t pl_ticket;
     cudaEvent_t ev_t0, ev_t1;
     // scratch

@@ -57,14 +57,18 @@ def test_empty_and_full_keypoint_buffers(fe, orc):
         nxt, st = fe.track([a], [b], [kp], None)
         ok = st[0] != 0
         assert ok.sum() >= 0.9 * len(kp) and np.abs(nxt[0][ok] - kp[ok]).max() < 1e-3
-        # keypoint buffer already full: no room for new corners, existing ones untouched
+        # The reference's keypoint vector is unbounded: a buffer too small for existing + new corners is an error
+        # (RDFE_ERR_OVERFLOW, "keypoint list truncated"), never a silently shorter list ...
+        from rd_vio_b200._native import FrontEndError
         full = kp[:10]
-        out = fe.detect([a], [full], 150, 20.0, stride=10)[0]
-        assert np.array_equal(out, full)
-        # room for exactly 3 more
-        out = fe.detect([a], [full], 150, 20.0, stride=13)[0]
         ref = orc.detect_keypoints(orc.clahe(img), full, 150, 20.0)[0]
-        assert np.array_equal(out, ref[:13])
+        assert len(ref) > 13
+        for too_small in (10, 13):
+            with pytest.raises(FrontEndError, match="truncated"):
+                fe.detect([a], [full], 150, 20.0, stride=too_small)
+        # ... the flag is cleared by the failing call, and a buffer that fits exactly is fine
+        out = fe.detect([a], [full], 150, 20.0, stride=len(ref))[0]
+        assert np.array_equal(out, ref)
     finally:
         fe.release(a)
         fe.release(b)

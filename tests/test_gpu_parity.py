@@ -304,7 +304,7 @@ def test_fused_step_equals_separate_calls(orc, stream0, frames0):
 
 
 def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
-    """rdfe_frontend_step_submit/_wait with two steps in flight == the per-call host API."""
+    """rdfe_frontend_step_submit/_wait with three steps in flight (the pipeline depth) == the per-call host API."""
     import ctypes as C
     from rd_vio_b200 import _native as N
     from rd_vio_b200.frontend import FrontEnd
@@ -317,8 +317,8 @@ def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
         # expectation: two consecutive steps through the separate host calls
         want = []
         carried = kps
-        for stp in range(2):
-            a, b = sets[stp], sets[stp + 1]
+        for stp in range(3):
+            a, b = sets[stp % 3], sets[(stp + 1) % 3]
             fe.preprocess(list(b), frames0[stp + 1:stp + 1 + n])
             nxt, st = fe.track(list(a), list(b), carried, None)
             merged = []
@@ -326,13 +326,13 @@ def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
                 merged.append(fe.detect([int(b[i])], [nxt[i][st[i] != 0]], 150, 20.0, stride=stride)[0])
             want.append((merged, st))
             carried = [m[:stride] for m in merged]
-        # pipelined: submit step 0 and step 1 back to back (step 1's input = step 0's expected output), then wait
-        imgs = [np.stack(frames0[s + 1:s + 1 + n]) for s in range(2)]
+        # pipelined: submit steps 0, 1, 2 back to back (each step's input = the previous step's expected output), then wait
+        imgs = [np.stack(frames0[s + 1:s + 1 + n]) for s in range(3)]
         tp, dp = fe.track_params(), fe.detect_params(max_points=150, keypoint_distance=20.0)
         tickets, bufs = [], []
-        inputs = [kps, want[0][0]]
-        for stp in range(2):
-            a, b = sets[stp], sets[stp + 1]
+        inputs = [kps, want[0][0], want[1][0]]
+        for stp in range(3):
+            a, b = sets[stp % 3], sets[(stp + 1) % 3]
             curr = np.zeros((n, stride, 2)); cnt = np.zeros(n, np.int32)
             for i in range(n):
                 c = inputs[stp][i][:stride]
@@ -342,7 +342,7 @@ def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
             N.check(L.rdfe_frontend_step_submit(fe.handle, a.ctypes.data, b.ctypes.data, n, ptrs, 752, 6.0, 8, 8, C.byref(tp),
                                                 curr.ctypes.data, None, cnt.ctypes.data, C.byref(dp), stride, C.byref(tk)), "submit")
             tickets.append(tk.value); bufs.append((curr, cnt, ptrs))
-        for stp in range(2):
+        for stp in range(3):
             out = np.zeros((n, stride, 2)); oc = np.zeros(n, np.int32); ost = np.zeros((n, stride), np.int8)
             N.check(L.rdfe_frontend_step_wait(fe.handle, tickets[stp], out.ctypes.data, oc.ctypes.data, ost.ctypes.data), "wait")
             for i in range(n):
