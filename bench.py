@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short BASELINE configs[2] (ADVIO-shaped) and configs[3] (1080p / 31x31) measurements")
     ap.add_argument("--other-steps", type=int, default=30, help="timed steps of each other_configs measurement")
+    ap.add_argument("--no-chained", action="store_true",
+                    help="skip the chained measurement (keypoints carried on the device from step to step, LK template cache off/on)")
     ap.add_argument("--no-compaction", action="store_true",
                     help="round-1 step semantics (lost tracks stay in the keypoint list); default = the reference's (frame.cpp:160-170)")
     return ap.parse_args()
@@ -201,7 +203,7 @@ def ncu_counters(workload, S):
     return {}
 
 
-def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e, want_timeline=""):
+def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e, want_timeline="", want_chained=False):
     """One workload on this rank's GPU: device-resident value, per-kernel times, e2e + copy-only legs."""
     import torch
     from rd_vio_b200 import _native as N
@@ -222,7 +224,8 @@ def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e
     torch.cuda.set_stream(tstream)
     # three slot sets in rotation (prev, new, next-new): lets the preprocess of step t+1 overlap step t
     NSETS = 3
-    fe = FrontEnd(W, H, wl["max_level"], wl["win"], num_slots=NSETS * S, max_points=max(stride, 512), device=local,
+    cstride = 1024 if want_chained else 0          # chained run: the list grows beyond 2 x points before it settles
+    fe = FrontEnd(W, H, wl["max_level"], wl["win"], num_slots=NSETS * S, max_points=max(stride, 512, cstride), device=local,
                   stream=tstream.cuda_stream)
     h = fe.handle
     slots = [np.array([fe.acquire() for _ in range(S)], np.int32) for _ in range(NSETS)]
@@ -356,6 +359,89 @@ def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e
             json.dump([{"kernel": L.rdfe_profile_kernel_name(kid[i]).decode(), "start_us": round(1e3 * t0s[i], 2),
                         "end_us": round(1e3 * t1s[i], 2)} for i in range(ncap.value)], f)
 
+    # ---- chained: what FeatureTracker::run does frame after frame -- the tracked + newly detected keypoints of step t
+    # ARE the carried keypoints of step t+1 (they never leave the device), predictions from the gyro rotation
+    # (rdfe_predict_rotation_dev = frame.cpp:82-93).  Only here can the LK template cache act (the headline run above
+    # restarts every step from the stored detections of its ring frame, as BASELINE's "150 carried" asks).
+    chained = None
+    if want_chained:
+        Hs = np.zeros((T, S, 9))
+        for i, sid in enumerate(stream_ids):
+            st = SyntheticStream(sid, W, H, period=T)
+            K = st.K(); Ki = np.linalg.inv(K)
+            for k in range(T):
+                Hs[k, i] = (K @ st.gyro_delta(k).T @ Ki).reshape(9)
+        H_dev = torch.from_numpy(Hs).cuda()
+        tpc = fe.track_params(has_prediction=1)
+        chained = {"stride": cstride}
+        for label, cache_on in (("cache_off", 0), ("cache_on", 1)):
+            N.check(L.rdfe_set_template_cache(h, cache_on), "set_template_cache")
+            bufs = [torch.zeros((S, cstride, 2), dtype=torch.float64, device="cuda") for _ in range(2)]
+            cnts = [torch.zeros((S,), dtype=torch.int32, device="cuda") for _ in range(2)]
+            cstatus = torch.zeros((S, cstride), dtype=torch.int8, device="cuda")
+            tt = t - (t % T) + T                      # start on ring frame 0
+            bufs[0][:, :stride] = curr_xy[0]
+            cnts[0].copy_(cnt[0])
+            N.check(L.rdfe_preprocess_batch_dev(h, slots[tt % NSETS].ctypes.data, S, dptrs[0], W, 6.0, 8, 8), "preprocess")
+            fe.sync()
+            hist = []
+
+            def cstep(tt, a):
+                k = tt % T
+                prev, new = slots[tt % NSETS], slots[(tt + 1) % NSETS]
+                cur, nxt, ccur, cnxt = bufs[a], bufs[a ^ 1], cnts[a], cnts[a ^ 1]
+                N.check(L.rdfe_predict_rotation_dev(h, S, vp(H_dev[k]), vp(cur), vp(ccur), cstride, vp(nxt)), "predict")
+                cnxt.copy_(ccur, non_blocking=True)
+                N.check(L.rdfe_frontend_step_dev(h, prev.ctypes.data, new.ctypes.data, S, dptrs[(k + 1) % T], W, 6.0, 8, 8,
+                                                 C.byref(tpc), vp(cur), vp(nxt), vp(ccur), vp(cstatus), C.byref(dp), vp(cnxt),
+                                                 cstride), "frontend_step(chained)")
+
+            a = 0
+            for _ in range(3 * T):                     # settle: the keypoint population reaches its steady state
+                cstep(tt, a); tt += 1; a ^= 1
+            fe.sync()
+            if cache_on:
+                L.rdfe_template_cache_stats(h, None, None, 1)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(steps):
+                cstep(tt, a); tt += 1; a ^= 1
+            c1.record()
+            barrier()
+            fe.sync()
+            cval, cms = PAR.aggregate_throughput(S * steps, c0.elapsed_time(c1), dist, torch.device("cuda", local))
+            res = {"value": cval, "unit": UNIT, "ms_per_step": cms / steps, "steps": steps,
+                   "mean_keypoints_after_step": float(cnts[a].float().mean().item())}
+            if cache_on:
+                lk_, hit_ = C.c_ulonglong(0), C.c_ulonglong(0)
+                N.check(L.rdfe_template_cache_stats(h, C.byref(lk_), C.byref(hit_), 1), "cache_stats")
+                res["tracked_points_per_frame"] = lk_.value / max(S * steps, 1)
+                res["cache_hit_frac"] = hit_.value / max(lk_.value, 1)
+            if rank == 0:            # serialised per-kernel times of this mode (LK is the kernel the cache changes)
+                N.check(L.rdfe_profile_enable(h, 1), "profile_enable")
+                for _ in range(10):
+                    cstep(tt, a); tt += 1; a ^= 1
+                nk = L.rdfe_profile_num_kernels()
+                pms = (C.c_double * nk)(); pn = (C.c_int64 * nk)()
+                N.check(L.rdfe_profile_collect(h, pms, pn), "profile_collect")
+                N.check(L.rdfe_profile_enable(h, 0), "profile_enable")
+                res["kernels_us_per_launch"] = {L.rdfe_profile_kernel_name(i).decode(): round(1e3 * pms[i] / pn[i], 1)
+                                                for i in range(nk) if pn[i] > 0}
+            else:
+                for _ in range(10):
+                    cstep(tt, a); tt += 1; a ^= 1
+                fe.sync()
+            chained[label] = res
+            t = tt
+        N.check(L.rdfe_set_template_cache(h, 0), "set_template_cache")
+        chained["how"] = ("device-resident, keypoints carried from step to step on the device (tracked survivors + new detections, "
+                          "frame.cpp:160-170), predictions by rdfe_predict_rotation_dev from the synthetic gyro increment; "
+                          "3 ring periods of settling before the timed steps; same kernels, streams and ring as `value`")
+        # leave the slot rotation where the e2e leg expects it
+        N.check(L.rdfe_preprocess_batch_dev(h, slots[t % NSETS].ctypes.data, S, dptrs[t % T], W, 6.0, 8, 8), "preprocess")
+        fe.sync()
+
     # ---- end to end through the host-pointer C ABI: pinned host frames + keypoints in, results out, every step
     e2e = None
     if want_e2e:
@@ -424,7 +510,7 @@ def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e
 
     out = {"workload": wl_name, "wl": wl, "S": S, "T": T, "steps": steps, "warmup": max(warmup, 3), "value": value, "ms_max": ms_max,
            "launches": int(launches), "clocks": clocks, "prof": prof, "e2e": e2e, "mean_pts": mean_pts, "tracked_ok": tracked_ok,
-           "new_per_frame": new_per_frame, "stream_ids": stream_ids}
+           "new_per_frame": new_per_frame, "stream_ids": stream_ids, "chained": chained}
     fe.close()
     del dev_frames, host_frames, curr_xy, pred_xy
     torch.cuda.empty_cache()
@@ -502,7 +588,7 @@ def main_b200(args, wl):
             os.close(saved_fd)
     env = {"rank": rank, "world": world, "local": local, "dist": dist}
     m = measure_gpu(args, env, args.workload, args.streams, args.ring, args.steps, args.warmup, args.profile_steps,
-                    not args.no_e2e, args.timeline)
+                    not args.no_e2e, args.timeline, want_chained=not args.no_chained and args.workload == "euroc")
     m["world"] = world
 
     # ---- BASELINE configs[2] / configs[3]: short measurements in the same process, every N (all ranks take part)
@@ -565,6 +651,7 @@ def main_b200(args, wl):
         "hbm_roofline_step": step,
         "kernels": m["prof"], "mean_carried_keypoints": m["mean_pts"], "tracked_ok_frac": m["tracked_ok"],
         "new_keypoints_per_frame": m["new_per_frame"],
+        "chained": m["chained"],
         "other_configs": other_cfgs,
         "scope_note": "the step is the plugin's three calls; Frame::track_keypoints' two host RANSAC masks (frame.cpp:99-132, "
                       "SURVEY 8(f) rank 2) between track and detect stay on the host and are NOT in the timed region of either arm",

@@ -177,6 +177,13 @@ RDFE_API int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const 
                            const int *dev_track_counts, char *dev_status, const rdfe_detect_params *dp,
                            int *dev_kp_counts, int stride);
 
+/* Caller-side helper for keypoints that stay on the device between steps: Frame::track_keypoints' prediction
+ * (frame.cpp:82-93) next_i = apply_k(delta_q * remove_k(curr_i, K), K_next) is the homography H = K_next R K^-1 applied
+ * to the pixel; dev_H holds one row-major 3x3 (doubles) per image.  dev_pred_xy may then be handed to
+ * rdfe_track_batch_dev / rdfe_frontend_step_dev as the prediction (has_prediction = 1). */
+RDFE_API int rdfe_predict_rotation_dev(rdfe_ctx *ctx, int n, const double *dev_H, const double *dev_curr_xy,
+                              const int *dev_counts, int stride, double *dev_pred_xy);
+
 /* "Next" row: the cv::undistort(img, out, K, D) the reference's dataset reader applies to
  * every frame before addFrame (examples/dataset.hpp:232-236, :591).  K: 3x3 row-major float32 camera matrix,
  * D: k1 k2 p1 p2 float32.  When set, every preprocess / frontend_step call first remaps its source frames with
@@ -201,6 +208,17 @@ RDFE_API int rdfe_set_input_format(rdfe_ctx *ctx, int channels);
  * others (environment variable RDFE_PRIO="pre,harris,select,lk,poisson" overrides the five levels); a caller stream
  * created with a high priority keeps its own small copies from queueing behind the large grids. */
 RDFE_API int rdfe_set_pipelining(rdfe_ctx *ctx, int on);
+
+/* LK template cache (off by default; costs num_slots * max_points * ~3 KB * levels of HBM).  The backward pass of a
+ * track call builds, at the tracked position q in the NEXT image, exactly the per-level template (I*32, Ix, Iy over the
+ * window, A11/A12/A22) that the forward pass of the following track call needs when that point is carried on
+ * unchanged (FeatureTracker::run: next frame's curr keypoints = this frame's tracked ones).  With the cache on it is
+ * kept, keyed by (image generation of the slot, float x, float y), and a forward pass that finds its point loads it
+ * instead of staging the I / dI patches and rebuilding.  Results are bit-identical with and without (the template is
+ * a pure function of image and position); any call that rewrites level 0 of a slot invalidates its records. */
+RDFE_API int rdfe_set_template_cache(rdfe_ctx *ctx, int on);
+/* forward passes that consulted the cache / found their point there, since creation or the last reset (waits for the context) */
+RDFE_API int rdfe_template_cache_stats(rdfe_ctx *ctx, unsigned long long *lookups, unsigned long long *hits, int reset);
 
 /* Fused step only: on (default) = lost tracks (status == 0) are dropped before detect, the reference's behaviour
  * (frame.cpp:160-170); off = every carried entry (prediction where tracking failed) stays in the list and keeps

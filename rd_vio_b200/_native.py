@@ -60,6 +60,9 @@ SYMBOLS = {
     "rdfe_set_input_format": (_i, [_vp, _i]),
     "rdfe_set_pipelining": (_i, [_vp, _i]),
     "rdfe_set_step_compaction": (_i, [_vp, _i]),
+    "rdfe_predict_rotation_dev": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "rdfe_set_template_cache": (_i, [_vp, _i]),
+    "rdfe_template_cache_stats": (_i, [_vp, _vp, _vp, _i]),
     "rdfe_frontend_step_submit": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _d, _i, _i, C.POINTER(TrackParams), _vp, _vp, _vp,
                                        C.POINTER(DetectParams), _i, C.POINTER(_i)]),
     "rdfe_frontend_step_wait": (_i, [_vp, _i, _vp, _vp, _vp]),

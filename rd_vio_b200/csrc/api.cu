@@ -58,6 +58,12 @@ static int make_tensor_maps(rdfe_ctx *ctx) {
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image level %d) failed: %d", l, (int)r); return RDFE_ERR_CUDA; }
+            // the template patch reads only win+1 rows: its own box keeps the over-fetch of the J box out of DRAM
+            cuuint32_t boxT[3] = {jw, (cuuint32_t)win + 1, 1};
+            r = enc(&ctx->tm_imgT[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr.img[l], dims, strides, boxT, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(template level %d) failed: %d", l, (int)r); return RDFE_ERR_CUDA; }
         }
         {
             // derivative plane: one uint32 element = (dx, dy) int16 pair; dims are the true
@@ -404,6 +410,8 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     for (int i = 0; i < 2 * kProfMax; ++i) CK(cudaEventCreate(&ctx->prof_ev[i]));
 #undef CK
     ctx->slot_used = (uint8_t *)calloc((size_t)cfg->num_slots, 1);
+    ctx->slot_gen = (unsigned *)calloc((size_t)cfg->num_slots, sizeof(unsigned));
+    ctx->gen_counter = 1;
     int rc = make_tensor_maps(ctx);
     if (rc != RDFE_OK) return fail(rc);
     *out = ctx;
@@ -458,6 +466,8 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     cudaFree(ctx->pf_gftt_xy); cudaFree(ctx->pf_gftt_resp); cudaFree(ctx->pf_gftt_counts);
     if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
     free(ctx->slot_used);
+    free(ctx->slot_gen);
+    cudaFree(ctx->tc_data); cudaFree(ctx->tc_A); cudaFree(ctx->tc_hdr); cudaFree(ctx->tc_stats);
     free(ctx->slot_new_step);
     delete ctx;
 }
@@ -630,6 +640,43 @@ int rdfe_detect_prefetch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_dete
     return RDFE_OK;
 }
 
+int rdfe_set_template_cache(rdfe_ctx *ctx, int on) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    { const int rc_all = sync_all_streams(ctx); if (rc_all) return rc_all; }
+    if (on && !ctx->tc_data) {
+        const size_t entries = (size_t)ctx->cfg.num_slots * ctx->cfg.max_points;
+        const size_t rec = lk_cache_record_bytes(ctx->pyr.win, ctx->pyr.nlevels);
+        if (cudaMalloc(&ctx->tc_data, entries * rec) != cudaSuccess || cudaMalloc(&ctx->tc_A, entries * ctx->pyr.nlevels * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc(&ctx->tc_hdr, entries * sizeof(float4)) != cudaSuccess || cudaMalloc(&ctx->tc_stats, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(ctx->tc_data); cudaFree(ctx->tc_A); cudaFree(ctx->tc_hdr);
+            ctx->tc_data = nullptr; ctx->tc_A = nullptr; ctx->tc_hdr = nullptr;
+            set_error("rdfe_set_template_cache: %zu MB for %zu (slot, point) records not available",
+                      (entries * (rec + 16 + ctx->pyr.nlevels * 16)) >> 20, entries);
+            return RDFE_ERR_NOMEM;
+        }
+        RDFE_CUDA_OK(cudaMemset(ctx->tc_hdr, 0, entries * sizeof(float4)));    // generation 0 never matches (slots start at >= 2)
+        RDFE_CUDA_OK(cudaMemset(ctx->tc_stats, 0, 2 * sizeof(unsigned long long)));
+    }
+    ctx->tc_on = on != 0;
+    return RDFE_OK;
+}
+
+int rdfe_template_cache_stats(rdfe_ctx *ctx, unsigned long long *lookups, unsigned long long *hits, int reset) {
+    if (!ctx) return RDFE_ERR_INVALID;
+    unsigned long long v[2] = {0, 0};
+    if (ctx->tc_stats) {
+        RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+        { const int rc_all = sync_all_streams(ctx); if (rc_all) return rc_all; }
+        RDFE_CUDA_OK(cudaMemcpy(v, ctx->tc_stats, sizeof v, cudaMemcpyDeviceToHost));
+        if (reset) RDFE_CUDA_OK(cudaMemset(ctx->tc_stats, 0, sizeof v));
+    }
+    if (lookups) *lookups = v[0];
+    if (hits) *hits = v[1];
+    return RDFE_OK;
+}
+
 int rdfe_set_step_compaction(rdfe_ctx *ctx, int on) {
     if (!ctx) return RDFE_ERR_INVALID;
     ctx->compact_tracked = on != 0;
@@ -717,6 +764,19 @@ int rdfe_track_batch(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots
             if (status[k]) { next_xy[2 * k] = tmp[2 * k]; next_xy[2 * k + 1] = tmp[2 * k + 1]; }
         }
     return RDFE_OK;
+}
+
+// Frame::track_keypoints' keypoint prediction (frame.cpp:82-93) for keypoints that stay on the device between steps:
+// next = apply_k(delta_q * bearing_i, K_next) with bearing_i = remove_k(curr_i, K) is the homography K_next R K^-1
+// applied to the pixel.  dev_H: [n][9] row-major doubles, one per stream.
+int rdfe_predict_rotation_dev(rdfe_ctx *ctx, int n, const double *dev_H, const double *dev_curr_xy, const int *dev_counts,
+                              int stride, double *dev_pred_xy) {
+    if (!ctx || !dev_H || !dev_curr_xy || !dev_counts || !dev_pred_xy || n < 1 || n > ctx->max_batch || stride < 1) {
+        set_error("rdfe_predict_rotation_dev: bad argument");
+        return RDFE_ERR_INVALID;
+    }
+    RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
+    return check_launch(ctx, launch_predict_rotation(ctx, n, dev_H, dev_curr_xy, dev_counts, stride, dev_pred_xy), "predict");
 }
 
 // ------------------------------------------------- fused per-frame step
@@ -1102,6 +1162,7 @@ int rdfe_upload_level0(rdfe_ctx *ctx, int slot, const uint8_t *image_with_halo, 
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
     { const int rc_all = sync_all_streams(ctx); if (rc_all) return rc_all; }
     ctx->pf_valid = false;
+    ctx->slot_gen[slot] = ++ctx->gen_counter;           // cached LK templates of the old pixels are stale
     uint8_t *dst = ctx->pyr.image_origin(0, slot) - (size_t)win * g.ipitch - win;
     RDFE_CUDA_OK(cudaMemcpy2D(dst, g.ipitch, image_with_halo, fw, fw, fh, cudaMemcpyHostToDevice));
     return RDFE_OK;
@@ -1207,7 +1268,7 @@ int rdfe_memcpy_d2h(rdfe_ctx *ctx, void *host_dst, const void *dev_src, size_t b
 
 static const char *const kKernelNames[K_COUNT] = {"clahe_hist_lut", "clahe_apply", "pyrdown", "scharr",
                                                   "harris_nms", "select", "lk_track", "poisson_append", "undistort",
-                                                  "harris_resolve"};
+                                                  "harris_resolve", "predict_rotation"};
 
 int rdfe_profile_num_kernels(void) { return K_COUNT; }
 const char *rdfe_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }

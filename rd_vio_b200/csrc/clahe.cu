@@ -346,6 +346,7 @@ clahe_apply_fast_kernel(const uint8_t *const *__restrict__ src, size_t pitch, Cl
 
 int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_src, size_t src_pitch,
                  int src_vec4, const ClaheParams &cp) {
+    for (int i = 0; i < slots.n; ++i) ctx->slot_gen[slots.v[i]] = ++ctx->gen_counter;   // level 0 is rewritten: cached LK templates of these slots are stale
     const int ntiles = cp.tiles_x * cp.tiles_y;
     dim3 g1(ntiles, slots.n);
     RDFE_LAUNCH(ctx, K_CLAHE_HIST, (clahe_hist_lut_kernel<<<g1, kHistWarps * 32, 0, ctx->ls>>>(d_src, src_pitch, src_vec4, cp, ctx->lut)));

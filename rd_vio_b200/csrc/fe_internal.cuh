@@ -153,7 +153,7 @@ inline int adaptive_strip_rows(int height, int warps_per_row_strip, int min_rows
 }
 
 enum KernelId {
-    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_HARRIS_RESOLVE, K_COUNT
+    K_CLAHE_HIST = 0, K_CLAHE_APPLY, K_PYRDOWN, K_SCHARR, K_HARRIS, K_SELECT, K_LK, K_POISSON, K_UNDISTORT, K_HARRIS_RESOLVE, K_PREDICT, K_COUNT
 };
 constexpr int kProfMax = 4096;      // timed launches between two rdfe_profile_collect calls
 
@@ -177,6 +177,14 @@ struct rdfe_ctx {
     size_t gray_pitch, gray_slot;  // geometry of the ingest output plane (und_plane)
     CUtensorMap tm_img[RDFE_MAX_LEVELS];
     CUtensorMap tm_der[RDFE_MAX_LEVELS];
+    CUtensorMap tm_imgT[RDFE_MAX_LEVELS];   // image, box = LK template patch (JW x (win+1))
+    // LK template cache (rdfe_set_template_cache): templates the backward pass built, keyed by (generation, x, y)
+    bool tc_on;
+    uint4 *tc_data;               // [num_slots][max_points][record]
+    float4 *tc_A, *tc_hdr;        // [num_slots][max_points][levels], [num_slots][max_points]
+    unsigned long long *tc_stats; // device [2]: lookups, hits
+    unsigned *slot_gen;           // [num_slots] host: bumped whenever level 0 of the slot is rewritten
+    unsigned gen_counter;
     cudaStream_t stream;
     bool own_stream;
     cudaStream_t ls;              // stream the kernel launchers currently enqueue on (stream or aux_stream)
@@ -305,6 +313,9 @@ int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, con
                           const char *d_lk_status /* optional: keep only status != 0 presets (frame.cpp:160-170) */);
 int launch_undistort(rdfe_ctx *ctx, int n, const uint8_t *const *d_src, size_t src_pitch, int src_vec4, uint8_t *const *d_dst,
                      size_t dst_pitch);
+size_t lk_cache_record_bytes(int win, int nlevels);
+int launch_predict_rotation(rdfe_ctx *ctx, int n, const double *d_H, const double *d_curr_xy, const int *d_counts, int stride,
+                            double *d_pred_xy);
 int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const rdfe_track_params &p,
               const double *d_curr_xy, double *d_next_xy, const int *d_counts, int stride, char *d_status);
 

@@ -20,8 +20,16 @@
 //     aligned 32-bit words only when the window's INTEGER origin moves, and re-paired with
 //     funnel shifts so that each bilinear sample is two IDP.2A (u16 x u8 dot products);
 //   * sums (A11,A12,A22,b1,b2) are accumulated as exact integers per lane and reduced with
-//     REDUX; one int64->float conversion.  (OpenCV accumulates in float32; the exact sum is the
-//     value that accumulation approximates -- measured deviation < 1e-3 px.)
+//     REDUX in 16-bit halves; fma(float(hi), 65536, float(lo)) rounds the exact total once (== int64->float).
+//     (OpenCV accumulates in float32; the exact sum is the value that accumulation approximates --
+//     measured deviation < 1e-3 px.)
+//   * forward and backward pass share ONE copy of the pyramid code (loop over the direction);
+//   * template cache (rdfe_set_template_cache): the backward pass of step t builds, per level, exactly the
+//     template (I*32, Ix, Iy over the window, A11/A12/A22) that the forward pass of step t+1 needs for a point
+//     carried unchanged.  It is stored (packed int16, coalesced 16-byte vectors) keyed by (slot generation,
+//     float x, float y); a forward pass that finds its point there loads 3 KB per level instead of staging the
+//     I and dI patches and rebuilding (~420 of ~1300 warp instructions per level pass), bit-identical by
+//     construction: the template is a pure function of (image, position).
 #include <cstdio>
 #include "fe_internal.cuh"
 
@@ -29,17 +37,28 @@ namespace rdfe {
 
 template <int WIN> struct LKCfg;
 template <> struct LKCfg<21> {
-    static constexpr int SEG = 7, NSEG = 3, JW = 48, JH = 32, DW = 28, DH = 22, MARGIN = 5, WARPS = 4, MIN_CTAS = 4;
+    static constexpr int SEG = 7, NSEG = 3, JW = 48, JH = 32, IH = 22, DW = 28, DH = 22, MARGIN = 5, WARPS = 4, MIN_CTAS = 4;
     static constexpr bool PACKED = false;
 };
 template <> struct LKCfg<31> {
-    static constexpr int SEG = 8, NSEG = 4, JW = 64, JH = 48, DW = 36, DH = 32, MARGIN = 8, WARPS = 4, MIN_CTAS = 3;
+    static constexpr int SEG = 8, NSEG = 4, JW = 64, JH = 48, IH = 32, DW = 36, DH = 32, MARGIN = 8, WARPS = 4, MIN_CTAS = 3;
     static constexpr bool PACKED = true;
 };
 
 struct LKMaps {
-    CUtensorMap img[RDFE_MAX_LEVELS];
+    CUtensorMap img[RDFE_MAX_LEVELS];     // J search region: box JW x JH
+    CUtensorMap imgT[RDFE_MAX_LEVELS];    // I template patch: box JW x (WIN+1) -- only the rows the template reads
     CUtensorMap der[RDFE_MAX_LEVELS];
+};
+
+// Template cache of one launch (all pointers null when the cache is off)
+struct LKCache {
+    uint4 *data;        // [slot][max_points][levels][ROUNDS*3][32] packed int16 templates
+    float4 *A;          // [slot][max_points][levels] (A11, A12, A22, flag bits: 1 = valid)
+    float4 *hdr;        // [slot][max_points] (x, y, generation bits, 1)
+    unsigned long long *stats;   // [2] forward passes that looked a point up / found it
+    int max_points, levels;
+    unsigned gen_curr[RDFE_MAX_BATCH], gen_next[RDFE_MAX_BATCH];   // generation of every image of the batch
 };
 
 struct LKParams {
@@ -48,6 +67,7 @@ struct LKParams {
     int lw[RDFE_MAX_LEVELS], lh[RDFE_MAX_LEVELS];
     int max_count;
     double eps2;
+    float eps2_lo, eps2_hi;         // eps2 * (1 -+ 1e-5): float pre-test brackets (the float sum is within 2e-7 of exact)
     float min_eig_thr;
     int border;
     double max_jump;                // rows / 4 (integer division)
@@ -103,6 +123,16 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
     return ((long long)shi << 16) + (long long)slo;
 }
 
+// float(exact warp sum) with ONE rounding: both half sums are exact in float (< 2^21), and the fma rounds
+// shi * 2^16 + slo once -- the same value as __ll2float_rn(warp_sum_exact(v)), without the 64-bit conversion.
+__device__ __forceinline__ float warp_sum_float(int v) {
+    const int hi = v >> 16;
+    const unsigned lo = (unsigned)v & 0xFFFFu;
+    const int shi = __reduce_add_sync(0xffffffffu, hi);
+    const unsigned slo = __reduce_add_sync(0xffffffffu, lo);
+    return __fmaf_rn((float)shi, 65536.f, (float)(int)slo);
+}
+
 // 9 consecutive bytes starting at byte offset `o` of a shared-memory buffer, as four
 // "pair words": P0 = bytes 0..3, P1 = 1..4, P2 = 4..7, P3 = 5..8.
 struct Pairs { unsigned p0, p1, p2, p3; };
@@ -132,11 +162,13 @@ __device__ __forceinline__ int dp2a_hi_s16_u8(unsigned w, unsigned px, int c) {
     return d;
 }
 // bilinear sample k (0..7) of a segment: top/bottom pair words, packed Q14 weights
+// `init` = 256 gives the reference's rounded sample; the iterations pass init = 256 - (Ival << 9), which makes
+// the result (sample - Ival) directly: Ival << 9 is a multiple of 2^9, so it passes through the floor shift.
 template <int K>
-__device__ __forceinline__ int sample(const Pairs &t, const Pairs &b, unsigned wt, unsigned wb) {
+__device__ __forceinline__ int sample(const Pairs &t, const Pairs &b, unsigned wt, unsigned wb, int init = 256) {
     const unsigned pt = (K < 4) ? ((K & 1) ? t.p1 : t.p0) : ((K & 1) ? t.p3 : t.p2);
     const unsigned pb = (K < 4) ? ((K & 1) ? b.p1 : b.p0) : ((K & 1) ? b.p3 : b.p2);
-    int acc = 256;                                        // + (1 << (W_BITS1-5-1))
+    int acc = init;                                       // 256 = (1 << (W_BITS1-5-1))
     if ((K & 2) == 0) { acc = dp2a_lo_s16_u8(wt, pt, acc); acc = dp2a_lo_s16_u8(wb, pb, acc); }
     else { acc = dp2a_hi_s16_u8(wt, pt, acc); acc = dp2a_hi_s16_u8(wb, pb, acc); }
     return acc >> 9;
@@ -145,27 +177,37 @@ __device__ __forceinline__ int sample(const Pairs &t, const Pairs &b, unsigned w
 template <int WIN>
 struct __align__(128) WarpSmem {
     using C = LKCfg<WIN>;
-    uint8_t ipatch[C::JW * C::JH];
+    uint8_t ipatch[(C::JW * C::IH + 127) / 128 * 128];
     uint8_t jreg[C::JW * C::JH + 128];
     uint32_t dpatch[C::DW * C::DH + 32];
     uint64_t bar;
 };
 
+// cvRound of a float in [0, 2^22): adding 1.5 * 2^23 rounds to nearest-even in the FADD itself (same result as
+// cvt.rni), on the FMA/ALU pipes instead of a quarter-rate F2I
+__device__ __forceinline__ int rint_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000; }
 __device__ __forceinline__ void q14_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11) {
-    iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
-    iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
-    iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+    iw00 = rint_small((1.f - a) * (1.f - b) * 16384.f);
+    iw01 = rint_small(a * (1.f - b) * 16384.f);
+    iw10 = rint_small((1.f - a) * b * 16384.f);
     iw11 = 16384 - iw00 - iw01 - iw10;
 }
 
+// ---- packed template record of one (lane, round): 12 words = 3 uint4.
+//   words [0, SEG):             (Iy << 16) | (Ix & 0xffff) of pixel k
+//   words [SEG, SEG + (SEG+1)/2): Ival of pixels 2q, 2q+1 as unsigned halves (0 <= Ival <= 8160)
 // One pyramidal LK pass A -> B for the warp's point.  (prevx, prevy): position in A (level 0);
 // (qx, qy): initial guess in / result out.  Returns the OpenCV status flag.
+// tc_ld / tcA_ld: cached templates of this point in A (null: build them); tc_st / tcA_st: where to store the
+// templates built here (null: do not store).
 template <int WIN>
-__device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps, const LKParams &P, int slotA, int slotB,
-                          float prevx, float prevy, float &qx, float &qy, int win_rt) {
+__device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps, const LKParams &P, int slotA, int slotB,
+                                          float prevx, float prevy, float &qx, float &qy, const uint4 *tc_ld,
+                                          const float4 *tcA_ld, uint4 *tc_st, float4 *tcA_st) {
     using C = LKCfg<WIN>;
     constexpr int SEG = C::SEG, NSEG = C::NSEG, JW = C::JW, JH = C::JH, DW = C::DW;
     constexpr int ITEMS = WIN * NSEG, ROUNDS = (ITEMS + 31) / 32;
+    constexpr int win_rt = WIN;
     const int lane = threadIdx.x & 31;
     const float half = (float)(WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
@@ -183,6 +225,7 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
         iseg[r] = tt - irow[r] * NSEG;
     }
 
+#pragma unroll 1
     for (int level = P.nlevels - 1; level >= 0; --level) {
         const int cols = P.lw[level], rows = P.lh[level];
         const float lscale = (float)(1. / (double)(1 << level));
@@ -192,13 +235,22 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
         else { nx = nxp * 2.f; ny = nyp * 2.f; }
         nxp = nx; nyp = ny;
 
+        if (tcA_st && lane == 0) tcA_st[level] = make_float4(0.f, 0.f, 0.f, 0.f);     // no template of this level (yet)
         px -= half; py -= half;
         const int ipx = (int)floorf(px), ipy = (int)floorf(py);
         if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows) {
             if (level == 0) status = 0;
             continue;
         }
-        // ---- stage I patch, dI patch and the J search region (16-B aligned box starts)
+        // a cached template of this level?  (warp-uniform: every lane reads the same record)
+        float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+        bool cached = false;
+        if (tcA_ld) {
+            const float4 a = __ldg(tcA_ld + level);
+            cached = __float_as_uint(a.w) == 1u;
+            A11 = a.x; A12 = a.y; A22 = a.z;
+        }
+        // ---- stage the J search region, and (if the template must be built) the I and dI patches (16-B aligned box starts)
         const int ixg = ipx + kHaloX, ixa = ixg & ~15, ioff = ixg - ixa;
         const int dxa = ipx & ~3, doff = ipx - dxa;
         int jx0, jy0;                                    // interior coordinates of the staged J region origin
@@ -209,22 +261,48 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
         }
         __syncwarp();
         if (lane == 0) {
-            mbar_expect_tx(&ws.bar, 2u * JW * JH + 4u * DW * C::DH);
-            tma_load_3d(ws.ipatch, &maps.img[level], ixa, ipy + win_rt, slotA, &ws.bar);
-            tma_load_3d(ws.dpatch, &maps.der[level], dxa, ipy, slotA, &ws.bar);
+            if (cached) {
+                mbar_expect_tx(&ws.bar, (uint32_t)(JW * JH));
+            } else {
+                mbar_expect_tx(&ws.bar, (uint32_t)(JW * JH + JW * C::IH) + 4u * DW * C::DH);
+                tma_load_3d(ws.ipatch, &maps.imgT[level], ixa, ipy + win_rt, slotA, &ws.bar);
+                tma_load_3d(ws.dpatch, &maps.der[level], dxa, ipy, slotA, &ws.bar);
+            }
             tma_load_3d(ws.jreg, &maps.img[level], jx0 + kHaloX, jy0 + win_rt, slotB, &ws.bar);
         }
-        mbar_wait(&ws.bar, phase);
-        phase ^= 1u;
 
-        // ---- template: Ival (I*32), Ix, Iy in registers; exact integer A sums
+        // ---- template in registers: Cv = 256 - (I*32 << 9) (so that a J sample started from it IS the difference), Ix, Iy
         int iw00, iw01, iw10, iw11;
-        q14_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
-        int Ival[ROUNDS][SEG];
+        int Cv[ROUNDS][SEG];
         int Ixv[ROUNDS][SEG];                            // PACKED: (Iy << 16) | (Ix & 0xffff)
         int Iyv[C::PACKED ? 1 : ROUNDS][C::PACKED ? 1 : SEG];
-        int a11 = 0, a12 = 0, a22 = 0;
-        {
+        if (cached) {
+            // 3 coalesced 16-byte loads per round while the J box is in flight
+            const uint4 *src = tc_ld + (size_t)level * (ROUNDS * 3 * 32) + lane;
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) {
+                unsigned w[12];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const uint4 v = __ldg(src + (r * 3 + m) * 32);
+                    w[4 * m] = v.x; w[4 * m + 1] = v.y; w[4 * m + 2] = v.z; w[4 * m + 3] = v.w;
+                }
+#pragma unroll
+                for (int k = 0; k < SEG; ++k) {
+                    const unsigned pv = w[SEG + (k >> 1)];
+                    const int iv = (k & 1) ? (int)(pv >> 16) : (int)(pv & 0xFFFFu);
+                    Cv[r][k] = 256 - (iv << 9);
+                    if constexpr (C::PACKED) Ixv[r][k] = (int)w[k];
+                    else { Ixv[r][k] = (int)(short)(w[k] & 0xFFFFu); Iyv[r][k] = (int)w[k] >> 16; }
+                }
+            }
+            mbar_wait(&ws.bar, phase);
+            phase ^= 1u;
+        } else {
+            mbar_wait(&ws.bar, phase);
+            phase ^= 1u;
+            q14_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
+            int a11 = 0, a12 = 0, a22 = 0;
             const unsigned wt = (unsigned)iw00 | ((unsigned)iw01 << 16), wb = (unsigned)iw10 | ((unsigned)iw11 << 16);  // iw11 may be -1
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) {
@@ -249,28 +327,48 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
                     int iy = (y00 * iw00 + y01 * iw01 + y10 * iw10 + y11 * iw11 + (1 << 13)) >> 14;
                     const bool ok = ivalid[r] && (iseg[r] * SEG + k < WIN);
                     if (!ok) { ix = 0; iy = 0; }
-                    Ival[r][k] = iv[k];
+                    Cv[r][k] = 256 - (iv[k] << 9);
                     if constexpr (C::PACKED) Ixv[r][k] = (iy << 16) | (ix & 0xFFFF);
                     else { Ixv[r][k] = ix; Iyv[r][k] = iy; }
                     a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
                     dt = dt1; db = db1;
                 }
+                if (tc_st) {
+                    unsigned w[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) w[k] = 0u;
+#pragma unroll
+                    for (int k = 0; k < SEG; ++k) {
+                        if constexpr (C::PACKED) w[k] = (unsigned)Ixv[r][k];
+                        else w[k] = ((unsigned)Iyv[r][k] << 16) | ((unsigned)Ixv[r][k] & 0xFFFFu);
+                    }
+#pragma unroll
+                    for (int q = 0; q < (SEG + 1) / 2; ++q)
+                        w[SEG + q] = (unsigned)iv[2 * q] | ((2 * q + 1 < SEG) ? ((unsigned)iv[2 * q + 1] << 16) : 0u);
+                    uint4 *dst = tc_st + (size_t)level * (ROUNDS * 3 * 32) + lane;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) dst[(r * 3 + m) * 32] = make_uint4(w[4 * m], w[4 * m + 1], w[4 * m + 2], w[4 * m + 3]);
+                }
             }
+            A11 = warp_sum_float(a11) * FLT_SCALE;
+            A12 = warp_sum_float(a12) * FLT_SCALE;
+            A22 = warp_sum_float(a22) * FLT_SCALE;
         }
-        const float A11 = __ll2float_rn(warp_sum_exact(a11)) * FLT_SCALE;
-        const float A12 = __ll2float_rn(warp_sum_exact(a12)) * FLT_SCALE;
-        const float A22 = __ll2float_rn(warp_sum_exact(a22)) * FLT_SCALE;
         float D = A11 * A22 - A12 * A12;
-        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
-        if (minEig < P.min_eig_thr || D < 1.1920928955078125e-07f) {
-            if (level == 0) status = 0;
-            continue;
+        if (!cached) {
+            const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+            if (minEig < P.min_eig_thr || D < 1.1920928955078125e-07f) {
+                if (level == 0) status = 0;
+                continue;
+            }
+            if (tcA_st && lane == 0) tcA_st[level] = make_float4(A11, A12, A22, __uint_as_float(1u));   // passed: reusable
         }
         D = 1.f / D;
         nx -= half; ny -= half;
         float pdx = 0.f, pdy = 0.f;
         int cinx = INT_MIN, ciny = INT_MIN;              // integer origin the cached J words belong to
         Pairs Jt[ROUNDS], Jb[ROUNDS];
+#pragma unroll 1
         for (int j = 0; j < P.max_count; ++j) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
@@ -304,30 +402,40 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
             int b1 = 0, b2 = 0;
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) {
-                int jv[8];
-                jv[0] = sample<0>(Jt[r], Jb[r], wt, wb); jv[1] = sample<1>(Jt[r], Jb[r], wt, wb);
-                jv[2] = sample<2>(Jt[r], Jb[r], wt, wb); jv[3] = sample<3>(Jt[r], Jb[r], wt, wb);
-                jv[4] = sample<4>(Jt[r], Jb[r], wt, wb); jv[5] = sample<5>(Jt[r], Jb[r], wt, wb);
-                jv[6] = sample<6>(Jt[r], Jb[r], wt, wb); jv[7] = sample<7>(Jt[r], Jb[r], wt, wb);
+                int df[8];                               // J sample - Ival, straight out of the dot products
+                df[0] = sample<0>(Jt[r], Jb[r], wt, wb, Cv[r][0]); df[1] = sample<1>(Jt[r], Jb[r], wt, wb, Cv[r][1]);
+                df[2] = sample<2>(Jt[r], Jb[r], wt, wb, Cv[r][2]); df[3] = sample<3>(Jt[r], Jb[r], wt, wb, Cv[r][3]);
+                df[4] = sample<4>(Jt[r], Jb[r], wt, wb, Cv[r][4]); df[5] = sample<5>(Jt[r], Jb[r], wt, wb, Cv[r][5]);
+                df[6] = sample<6>(Jt[r], Jb[r], wt, wb, Cv[r][6]);
+                if constexpr (SEG > 7) df[7] = sample<7>(Jt[r], Jb[r], wt, wb, Cv[r][SEG - 1]);
 #pragma unroll
                 for (int k = 0; k < SEG; ++k) {
-                    const int diff = jv[k] - Ival[r][k];
                     if constexpr (C::PACKED) {
-                        b1 += diff * (int)(short)(Ixv[r][k] & 0xFFFF);
-                        b2 += diff * (Ixv[r][k] >> 16);
+                        b1 += df[k] * (int)(short)(Ixv[r][k] & 0xFFFF);
+                        b2 += df[k] * (Ixv[r][k] >> 16);
                     } else {
-                        b1 += diff * Ixv[r][k];
-                        b2 += diff * Iyv[r][k];
+                        b1 += df[k] * Ixv[r][k];
+                        b2 += df[k] * Iyv[r][k];
                     }
                 }
             }
-            const float fb1 = __ll2float_rn(warp_sum_exact(b1)) * FLT_SCALE;
-            const float fb2 = __ll2float_rn(warp_sum_exact(b2)) * FLT_SCALE;
+            const float fb1 = warp_sum_float(b1) * FLT_SCALE;
+            const float fb2 = warp_sum_float(b2) * FLT_SCALE;
             const float dx = (A12 * fb2 - A22 * fb1) * D, dy = (A12 * fb1 - A11 * fb2) * D;
             nx += dx; ny += dy;
             nxp = nx + half; nyp = ny + half;
-            if ((double)dx * (double)dx + (double)dy * (double)dy <= P.eps2) break;
-            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+            // |delta|^2 <= eps^2 is evaluated in double by the reference; the float sum is within 2e-7 of the exact
+            // value, so outside the +-1e-5 bracket around eps^2 the float test decides and the doubles are skipped
+            {
+                const float s2 = dx * dx + dy * dy;
+                bool conv;
+                if (s2 > P.eps2_hi) conv = false;
+                else if (s2 < P.eps2_lo) conv = true;
+                else conv = (double)dx * (double)dx + (double)dy * (double)dy <= P.eps2;
+                if (conv) break;
+            }
+            // fabs((double)(a + b)) < 0.01  <=>  fabsf(a + b) <= 0.01f  (0.01f is the largest float below the double 0.01)
+            if (j > 0 && fabsf(dx + pdx) <= 0.01f && fabsf(dy + pdy) <= 0.01f) {
                 nxp -= dx * 0.5f; nyp -= dy * 0.5f;
                 break;
             }
@@ -342,17 +450,19 @@ __device__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps
     return status;
 }
 
-template <int WIN>
-__global__ void __launch_bounds__(LKCfg<WIN>::WARPS * 32, LKCfg<WIN>::MIN_CTAS)
-lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKParams P, SlotList curr, SlotList next,
-                const double *__restrict__ curr_xy, double *__restrict__ next_xy, const int *__restrict__ counts,
-                char *__restrict__ status_out) {
+template <int WIN, int CTAS>
+__global__ void __launch_bounds__(LKCfg<WIN>::WARPS * 32, CTAS)
+lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKParams P, const __grid_constant__ SlotList curr,
+                const __grid_constant__ SlotList next, const __grid_constant__ LKCache tc, const double *__restrict__ curr_xy,
+                double *__restrict__ next_xy, const int *__restrict__ counts, char *__restrict__ status_out) {
     using C = LKCfg<WIN>;
+    constexpr int ROUNDS = (WIN * C::NSEG + 31) / 32;
     __shared__ WarpSmem<WIN> smem[C::WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int i = blockIdx.x * C::WARPS + warp;
-    if (i >= min(counts[b], P.stride)) return;
+    const int npts = min(counts[b], P.stride);
+    if (i >= npts) return;
     WarpSmem<WIN> &ws = smem[warp];
     if (lane == 0) {
         mbar_init(&ws.bar, 1);
@@ -364,18 +474,72 @@ lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKP
     const float cx = (float)curr_xy[2 * idx], cy = (float)curr_xy[2 * idx + 1];
     float qx = cx, qy = cy;
     if (P.has_prediction) { qx = (float)next_xy[2 * idx]; qy = (float)next_xy[2 * idx + 1]; }
+    const int slotA = curr.v[b], slotB = next.v[b];
 
-    int st = lk_pyramid<WIN>(ws, phase, maps, P, curr.v[b], next.v[b], cx, cy, qx, qy, WIN);
-    if (qx < (float)P.border || qx >= (float)(P.W - P.border) || qy < (float)P.border || qy >= (float)(P.H - P.border)) st = 0;
-    if (st) {
-        const float dx = qx - cx, dy = qy - cy;
-        if (sqrt((double)dx * (double)dx + (double)dy * (double)dy) > P.max_jump) st = 0;
+    // ---- template cache: is this point (same image generation, same float position) in the records the backward
+    // pass of the previous step left for slot A?  Carried points sit at or after their new index (lost ones before
+    // them were dropped), so the search walks upwards from i, 32 records per probe.
+    const uint4 *tc_ld = nullptr;
+    const float4 *tcA_ld = nullptr;
+    uint4 *tc_st = nullptr;
+    float4 *tcA_st = nullptr;
+    const size_t rec = (size_t)tc.levels * (ROUNDS * 3 * 32);       // uint4 per point
+    if (tc.data) {
+        const float4 *hdr = tc.hdr + (size_t)slotA * tc.max_points;
+        const unsigned gen = tc.gen_curr[b];
+        int found = -1;
+        for (int base = i; base < tc.max_points && base < i + 128 && found < 0; base += 32) {
+            const int j = base + lane;
+            bool hit = false;
+            if (j < tc.max_points) {
+                const float4 h = __ldg(hdr + j);
+                hit = h.x == cx && h.y == cy && __float_as_uint(h.z) == gen && __float_as_uint(h.w) == 1u;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) found = base + __ffs(m) - 1;
+        }
+        if (lane == 0) {
+            atomicAdd(tc.stats, 1ull);
+            if (found >= 0) atomicAdd(tc.stats + 1, 1ull);
+        }
+        if (found >= 0) {
+            const size_t e = (size_t)slotA * tc.max_points + found;
+            tc_ld = tc.data + e * rec;
+            tcA_ld = tc.A + e * tc.levels;
+        }
     }
-    if (st) {
-        float rx = cx, ry = cy;
-        const int rst = lk_pyramid<WIN>(ws, phase, maps, P, next.v[b], curr.v[b], qx, qy, rx, ry, WIN);
-        const float dx = cx - rx, dy = cy - ry;
-        if (!rst || sqrt((double)dx * (double)dx + (double)dy * (double)dy) > P.max_round_trip) st = 0;
+
+    // forward (dir 0: curr -> next from the prediction) and backward (dir 1: next -> curr seeded with curr) run through
+    // ONE inlined copy of the pyramid code: the arguments are selected by `dir`
+    int st = 1;
+#pragma unroll 1
+    for (int dir = 0; dir < 2; ++dir) {
+        const int sA = dir ? slotB : slotA, sB = dir ? slotA : slotB;
+        const float fromx = dir ? qx : cx, fromy = dir ? qy : cy;
+        float gx = dir ? cx : qx, gy = dir ? cy : qy;
+        const int rst = lk_pyramid<WIN>(ws, phase, maps, P, sA, sB, fromx, fromy, gx, gy, dir ? nullptr : tc_ld, dir ? nullptr : tcA_ld,
+                                        dir ? tc_st : nullptr, dir ? tcA_st : nullptr);
+        if (dir == 0) {
+            st = rst;
+            qx = gx; qy = gy;
+            if (qx < (float)P.border || qx >= (float)(P.W - P.border) || qy < (float)P.border || qy >= (float)(P.H - P.border)) st = 0;
+            if (st) {
+                const float dx = qx - cx, dy = qy - cy;
+                if (sqrt((double)dx * (double)dx + (double)dy * (double)dy) > P.max_jump) st = 0;
+            }
+            if (!st) break;
+            if (tc.data && i < tc.max_points) {
+                const size_t e = (size_t)slotB * tc.max_points + i;
+                tc_st = tc.data + e * rec;
+                tcA_st = tc.A + e * tc.levels;
+            }
+        } else {
+            const float dx = cx - gx, dy = cy - gy;
+            if (!rst || sqrt((double)dx * (double)dx + (double)dy * (double)dy) > P.max_round_trip) st = 0;
+            // the templates just built belong to (image B, position q): next step's forward pass looks them up
+            if (tc_st && lane == 0)
+                tc.hdr[(size_t)slotB * tc.max_points + i] = make_float4(qx, qy, __uint_as_float(tc.gen_next[b]), __uint_as_float(1u));
+        }
     }
     if (lane == 0) {
         status_out[idx] = (char)st;
@@ -390,6 +554,7 @@ int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const r
     const Pyramid &pyr = ctx->pyr;
     for (int l = 0; l < pyr.nlevels; ++l) {
         maps.img[l] = ctx->tm_img[l];
+        maps.imgT[l] = ctx->tm_imgT[l];
         maps.der[l] = ctx->tm_der[l];
         P.lw[l] = pyr.lv[l].w;
         P.lh[l] = pyr.lv[l].h;
@@ -400,25 +565,65 @@ int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const r
     double eps = p.epsilon; eps = eps < 0 ? 0 : eps > 10 ? 10 : eps;
     P.max_count = mc;
     P.eps2 = eps * eps;
+    P.eps2_lo = (float)(P.eps2 * (1.0 - 1e-5));
+    P.eps2_hi = (float)(P.eps2 * (1.0 + 1e-5));
     P.min_eig_thr = (float)p.min_eig_threshold;
     P.border = p.border;
     P.max_jump = (double)(P.H / 4);
     P.max_round_trip = p.max_round_trip;
     P.has_prediction = p.has_prediction;
     P.stride = stride;
+    LKCache tc;
+    memset(&tc, 0, sizeof tc);
+    if (ctx->tc_on && ctx->tc_data) {
+        tc.data = ctx->tc_data; tc.A = ctx->tc_A; tc.hdr = ctx->tc_hdr; tc.stats = ctx->tc_stats;
+        tc.max_points = ctx->cfg.max_points; tc.levels = pyr.nlevels;
+        for (int i = 0; i < curr.n; ++i) {
+            tc.gen_curr[i] = ctx->slot_gen[curr.v[i]];
+            tc.gen_next[i] = ctx->slot_gen[next.v[i]];
+        }
+    }
     if (pyr.win == 21) {
         dim3 grid((stride + LKCfg<21>::WARPS - 1) / LKCfg<21>::WARPS, curr.n);
-        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->ls>>>(maps, P, curr, next, d_curr_xy,
-                                                                                                      d_next_xy, d_counts, d_status)));
+        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21, LKCfg<21>::MIN_CTAS><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->ls>>>(
+                                   maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
     } else if (pyr.win == 31) {
         dim3 grid((stride + LKCfg<31>::WARPS - 1) / LKCfg<31>::WARPS, curr.n);
-        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->ls>>>(maps, P, curr, next, d_curr_xy,
-                                                                                                      d_next_xy, d_counts, d_status)));
+        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31, LKCfg<31>::MIN_CTAS><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->ls>>>(
+                                   maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
     } else {
         set_error("LK window %d unsupported (21 or 31)", pyr.win);
         return RDFE_ERR_UNSUPPORTED;
     }
     return 1;
+}
+
+// ---- caller-side prediction for keypoints that never leave the device (frame.cpp:82-93): pixel -> unit bearing through
+// K^-1, rotation by the pre-integrated gyro increment, back through K_next = one 3x3 homography per stream, float64.
+__global__ void predict_rotation_kernel(const double *__restrict__ H, const double *__restrict__ curr_xy, const int *__restrict__ counts,
+                                        int stride, double *__restrict__ pred_xy) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(counts[b], stride)) return;
+    const double *h = H + 9 * b;
+    const size_t k = ((size_t)b * stride + i) * 2;
+    const double x = curr_xy[k], y = curr_xy[k + 1];
+    const double X = h[0] * x + h[1] * y + h[2], Y = h[3] * x + h[4] * y + h[5], Z = h[6] * x + h[7] * y + h[8];
+    pred_xy[k] = X / Z;
+    pred_xy[k + 1] = Y / Z;
+}
+
+int launch_predict_rotation(rdfe_ctx *ctx, int n, const double *d_H, const double *d_curr_xy, const int *d_counts, int stride,
+                            double *d_pred_xy) {
+    dim3 grid((stride + 127) / 128, n);
+    RDFE_LAUNCH(ctx, K_PREDICT, (predict_rotation_kernel<<<grid, 128, 0, ctx->ls>>>(d_H, d_curr_xy, d_counts, stride, d_pred_xy)));
+    return 1;
+}
+
+// bytes of template-cache storage one (slot, point) needs for this context's window / level count
+size_t lk_cache_record_bytes(int win, int nlevels) {
+    const int nseg = win == 21 ? LKCfg<21>::NSEG : LKCfg<31>::NSEG;
+    const int rounds = (win * nseg + 31) / 32;
+    return (size_t)nlevels * rounds * 3 * 32 * sizeof(uint4);
 }
 
 }  // namespace rdfe

@@ -83,6 +83,16 @@ class FrontEnd:
         D = np.ascontiguousarray(np.asarray(D, np.float32).reshape(-1)[:4])
         N.check(self._L.rdfe_set_undistort(self._h, _vp(K), _vp(D)), "rdfe_set_undistort")
 
+    def set_template_cache(self, on: bool = True):
+        """LK template cache (rdfe_set_template_cache): the backward pass's templates serve the next forward pass."""
+        N.check(self._L.rdfe_set_template_cache(self._h, 1 if on else 0), "rdfe_set_template_cache")
+
+    def template_cache_stats(self, reset=False):
+        """(lookups, hits) of the LK template cache since creation / the last reset."""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        N.check(self._L.rdfe_template_cache_stats(self._h, C.byref(a), C.byref(b), 1 if reset else 0), "rdfe_template_cache_stats")
+        return int(a.value), int(b.value)
+
     def set_input_format(self, channels: int):
         """1 = gray (default), 3 = BGR, 4 = BGRA: cv::cvtColor of Odometry::addFrame (rdvio.hpp:42-49) on the device."""
         N.check(self._L.rdfe_set_input_format(self._h, int(channels)), "rdfe_set_input_format")

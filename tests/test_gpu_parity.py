@@ -310,15 +310,16 @@ def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
     from rd_vio_b200.frontend import FrontEnd
     L = N.lib()
     n, stride = 2, 300
-    with FrontEnd(752, 480, 3, 21, num_slots=3 * n, max_points=512) as fe:
-        sets = [np.array([fe.acquire() for _ in range(n)], np.int32) for _ in range(3)]
+    with FrontEnd(752, 480, 3, 21, num_slots=4 * n, max_points=512) as fe:
+        # four slot sets: no step rewrites a set the expectation phase still needs
+        sets = [np.array([fe.acquire() for _ in range(n)], np.int32) for _ in range(4)]
         fe.preprocess(list(sets[0]), frames0[0:n])
         kps = fe.detect(list(sets[0]), [np.zeros((0, 2))] * n, 150, 20.0)
-        # expectation: two consecutive steps through the separate host calls
+        # expectation: three consecutive steps through the separate host calls
         want = []
         carried = kps
         for stp in range(3):
-            a, b = sets[stp % 3], sets[(stp + 1) % 3]
+            a, b = sets[stp], sets[stp + 1]
             fe.preprocess(list(b), frames0[stp + 1:stp + 1 + n])
             nxt, st = fe.track(list(a), list(b), carried, None)
             merged = []
@@ -332,7 +333,7 @@ def test_pipelined_host_step_equals_separate_calls(orc, stream0, frames0):
         tickets, bufs = [], []
         inputs = [kps, want[0][0], want[1][0]]
         for stp in range(3):
-            a, b = sets[stp % 3], sets[(stp + 1) % 3]
+            a, b = sets[stp], sets[stp + 1]
             curr = np.zeros((n, stride, 2)); cnt = np.zeros(n, np.int32)
             for i in range(n):
                 c = inputs[stp][i][:stride]
