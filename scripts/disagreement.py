@@ -30,6 +30,12 @@ ap.add_argument("--workloads", default="euroc,advio,hd")
 a = ap.parse_args()
 
 
+def ordered(v):
+    """float32 -> integer that is monotone in the value (so that differences count ulps across the sign change too)"""
+    b = int(np.float32(v).view(np.int32))
+    return b if b >= 0 else -(b & 0x7FFFFFFF)
+
+
 def setdiff(p, q):
     ps = {(float(x), float(y)) for x, y in p}
     qs = {(float(x), float(y)) for x, y in q}
@@ -84,7 +90,7 @@ for name in a.workloads.split(","):
                         acc["harris_px"] += Rc.size
                         acc["harris_px_diff_vs_plain_cv2"] += len(dd)
                         for yy, xx in dd:
-                            u = abs(int(Rc[yy, xx].view(np.int32)) - int(Rg[yy, xx].view(np.int32)))
+                            u = abs(ordered(Rc[yy, xx]) - ordered(Rg[yy, xx]))
                             acc["harris_max_ulp_vs_plain_cv2"] = max(acc["harris_max_ulp_vs_plain_cv2"], u)
                 finally:
                     cv2.setUseOptimized(True)
