@@ -124,25 +124,30 @@ select_kernel(DetectScratch det, SelectParams sp, Pyramid pyr, SlotList slots, f
         if (tid == 0) s_count = 0;
         __syncthreads();
         unsigned long long *dst = (round & 1) ? bufA : bufB;
-        for (unsigned base = warp * 32; base < ncur; base += SEL_THREADS) {
-            const unsigned i = base + lane;
-            unsigned long long k = 0;
-            bool ok = false;
-            if (i < ncur) {
-                k = src[i];
-                ok = (unsigned)(k >> 32) > thr_bits && k < hi;
+        // four keys per lane are requested before the first one is used: the pass is bound by the latency of these loads
+        for (unsigned base0 = warp * 32; base0 < ncur; base0 += 4 * SEL_THREADS) {
+            unsigned long long kq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned i = base0 + u * SEL_THREADS + lane;
+                kq[u] = (i < ncur) ? src[i] : 0ull;
             }
-            if (ok && sp.use_min_dist && nacc0 > 0) {
-                const unsigned addr = (unsigned)k;
-                const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
-                ok = grid_pass(cellpts, sp.gw, sp.gh, sp.cell, sp.min_dist2, x, y);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (m) {
-                unsigned pos = 0;
-                if (lane == 0) pos = atomicAdd(&s_count, (unsigned)__popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-                if (ok) dst[pos] = k;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long k = kq[u];
+                bool ok = (unsigned)(k >> 32) > thr_bits && k < hi;      // k = 0 (beyond the list) fails the first test
+                if (ok && sp.use_min_dist && nacc0 > 0) {
+                    const unsigned addr = (unsigned)k;
+                    const int y = (int)(addr / (unsigned)W), x = (int)(addr - (unsigned)y * (unsigned)W);
+                    ok = grid_pass(cellpts, sp.gw, sp.gh, sp.cell, sp.min_dist2, x, y);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (m) {
+                    unsigned pos = 0;
+                    if (lane == 0) pos = atomicAdd(&s_count, (unsigned)__popc(m));
+                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                    if (ok) dst[pos] = k;
+                }
             }
         }
         __syncthreads();
@@ -154,8 +159,105 @@ select_kernel(DetectScratch det, SelectParams sp, Pyramid pyr, SlotList slots, f
         const unsigned n = ncur;                      // every key of the compacted list is eligible
         const unsigned long long *keys = src;
 
-        // ---- exact radix select of the SEL_CAP-th largest eligible key
+        // Bitonic sort of batch[0, cnt) (descending), used for the pivot sample and for the batch itself.
+        auto sort_batch = [&](unsigned cnt) {
+        unsigned N = 32;
+        while (N < cnt) N <<= 1;
+        for (unsigned i = cnt + tid; i < N; i += SEL_THREADS) batch[i] = 0ull;
+        __syncthreads();
+        // Bitonic sort, descending.  Thread t owns elements 2t and 2t+1 for the exchange distances j <= 32 (its
+        // partner for distance j is lane t ^ (j/2): register shuffles, no barrier); distances >= 64 go through
+        // shared memory.  All merges up to k2 = 64 stay inside one warp's 64 elements.
+        {
+            const unsigned half = N >> 1;
+            const bool warp_on = (unsigned)(warp * 32) < half;            // warp-uniform
+            const bool own = (unsigned)tid < half;
+            const unsigned e_idx = 2u * (unsigned)tid;
+            unsigned long long e0 = 0ull, e1 = 0ull;
+            auto reg_stages = [&](unsigned k2, unsigned jstart) {
+                const bool desc = (e_idx & k2) == 0;
+                for (unsigned j = jstart; j >= 2; j >>= 1) {
+                    const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, e0, (int)(j >> 1));
+                    const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, e1, (int)(j >> 1));
+                    const bool keep_max = ((e_idx & j) == 0) == desc;
+                    e0 = keep_max ? (e0 > p0 ? e0 : p0) : (e0 < p0 ? e0 : p0);
+                    e1 = keep_max ? (e1 > p1 ? e1 : p1) : (e1 < p1 ? e1 : p1);
+                }
+                const unsigned long long hi = e0 > e1 ? e0 : e1, lo = e0 > e1 ? e1 : e0;
+                e0 = desc ? hi : lo;
+                e1 = desc ? lo : hi;
+            };
+            if (warp_on) {
+                if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
+                for (unsigned k2 = 2; k2 <= min(N, 64u); k2 <<= 1) reg_stages(k2, k2 >> 1);
+                if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
+            }
+            __syncthreads();
+            for (unsigned k2 = 128; k2 <= N; k2 <<= 1) {
+                for (unsigned j = k2 >> 1, lj = 31 - __clz(k2 >> 1); j >= 64; j >>= 1, --lj) {
+                    if (own) {
+                        const unsigned t = (unsigned)tid;
+                        const unsigned i = ((t >> lj) << (lj + 1)) | (t & (j - 1u));
+                        const unsigned q = i + j;
+                        const unsigned long long a = batch[i], c = batch[q];
+                        const bool desc = ((i & k2) == 0);
+                        if (desc ? (a < c) : (a > c)) { batch[i] = c; batch[q] = a; }
+                    }
+                    __syncthreads();
+                }
+                if (warp_on) {
+                    if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
+                    reg_stages(k2, 32u);
+                    if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
+                }
+                __syncthreads();
+            }
+        }
+        };
+        // ---- pivot for the next batch.  ANY threshold lo gives an exact batch (the keys >= lo are a prefix of the
+        // descending order) as long as at most SEL_CAP keys pass it, so the pivot comes from a sorted sample of <= SEL_CAP
+        // keys taken at a regular stride (one short pass + one small sort instead of four full histogram passes); the
+        // gather below counts what passes, and if a pivot lets too many through the next, stricter one is tried; the exact
+        // radix select remains as the last resort.
         unsigned long long lo = 0;
+        unsigned long long pv[3] = {0ull, 0ull, 0ull};
+        int npv = 0;
+        if (n_el > SEL_CAP) {
+            const unsigned stride_s = (n_el + SEL_CAP - 1) / SEL_CAP;
+            const unsigned ns = (n_el + stride_s - 1) / stride_s;
+            for (unsigned i = tid; i < ns; i += SEL_THREADS) batch[i] = keys[(size_t)i * stride_s];
+            __syncthreads();
+            sort_batch(ns);
+            // expected number of keys >= sample[r] is about (r + 1) * stride: aim at 5/8, then 5/16, then 5/64 of the batch
+            const unsigned r0 = (SEL_CAP * 5u / 8u) / stride_s;
+            pv[0] = batch[min(max(r0, 1u), ns - 1u)];
+            pv[1] = batch[min(max(r0 / 2u, 1u), ns - 1u)];
+            pv[2] = batch[min(max(r0 / 8u, 1u), ns - 1u)];
+            npv = 3;
+            __syncthreads();
+        }
+        bool gathered = false;
+        for (int tr = 0; tr < npv && !gathered; ++tr) {
+            if (tid == 0) s_nb = 0;
+            __syncthreads();
+            const unsigned long long pivot = pv[tr];
+            for (unsigned i0 = tid; i0 < n; i0 += 4 * SEL_THREADS) {
+                unsigned long long kq[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) kq[u] = (i0 + u * SEL_THREADS < n) ? keys[i0 + u * SEL_THREADS] : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (kq[u] >= pivot && kq[u] != 0ull) {
+                        const unsigned pos = atomicAdd(&s_nb, 1u);
+                        if (pos < SEL_CAP) batch[pos] = kq[u];
+                    }
+            }
+            __syncthreads();
+            gathered = s_nb <= SEL_CAP;                    // block-uniform
+            __syncthreads();
+        }
+        if (!gathered) {
+        // ---- exact radix select of the SEL_CAP-th largest eligible key (last resort, and the whole list when it fits)
         if (n_el > SEL_CAP) {
             if (tid == 0) { s_prefix = 0; s_k = SEL_CAP; }
             unsigned long long mask = 0;
@@ -222,67 +324,21 @@ select_kernel(DetectScratch det, SelectParams sp, Pyramid pyr, SlotList slots, f
         // ---- gather [lo, hi) and sort descending
         if (tid == 0) s_nb = 0;
         __syncthreads();
-        for (unsigned i = tid; i < n; i += SEL_THREADS) {
-            const unsigned long long k = keys[i];
-            if (k >= lo) {
-                const unsigned pos = atomicAdd(&s_nb, 1u);
-                if (pos < SEL_CAP) batch[pos] = k;
-            }
+        for (unsigned i0 = tid; i0 < n; i0 += 4 * SEL_THREADS) {
+            unsigned long long kq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kq[u] = (i0 + u * SEL_THREADS < n) ? keys[i0 + u * SEL_THREADS] : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (kq[u] >= lo && kq[u] != 0ull) {
+                    const unsigned pos = atomicAdd(&s_nb, 1u);
+                    if (pos < SEL_CAP) batch[pos] = kq[u];
+                }
         }
         __syncthreads();
+        }   // !gathered
         const unsigned nb = min(s_nb, (unsigned)SEL_CAP);
-        unsigned N = 32;
-        while (N < nb) N <<= 1;
-        for (unsigned i = nb + tid; i < N; i += SEL_THREADS) batch[i] = 0ull;
-        __syncthreads();
-        // Bitonic sort, descending.  Thread t owns elements 2t and 2t+1 for the exchange distances j <= 32 (its
-        // partner for distance j is lane t ^ (j/2): register shuffles, no barrier); distances >= 64 go through
-        // shared memory.  All merges up to k2 = 64 stay inside one warp's 64 elements.
-        {
-            const unsigned half = N >> 1;
-            const bool warp_on = (unsigned)(warp * 32) < half;            // warp-uniform
-            const bool own = (unsigned)tid < half;
-            const unsigned e_idx = 2u * (unsigned)tid;
-            unsigned long long e0 = 0ull, e1 = 0ull;
-            auto reg_stages = [&](unsigned k2, unsigned jstart) {
-                const bool desc = (e_idx & k2) == 0;
-                for (unsigned j = jstart; j >= 2; j >>= 1) {
-                    const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, e0, (int)(j >> 1));
-                    const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, e1, (int)(j >> 1));
-                    const bool keep_max = ((e_idx & j) == 0) == desc;
-                    e0 = keep_max ? (e0 > p0 ? e0 : p0) : (e0 < p0 ? e0 : p0);
-                    e1 = keep_max ? (e1 > p1 ? e1 : p1) : (e1 < p1 ? e1 : p1);
-                }
-                const unsigned long long hi = e0 > e1 ? e0 : e1, lo = e0 > e1 ? e1 : e0;
-                e0 = desc ? hi : lo;
-                e1 = desc ? lo : hi;
-            };
-            if (warp_on) {
-                if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
-                for (unsigned k2 = 2; k2 <= min(N, 64u); k2 <<= 1) reg_stages(k2, k2 >> 1);
-                if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
-            }
-            __syncthreads();
-            for (unsigned k2 = 128; k2 <= N; k2 <<= 1) {
-                for (unsigned j = k2 >> 1, lj = 31 - __clz(k2 >> 1); j >= 64; j >>= 1, --lj) {
-                    if (own) {
-                        const unsigned t = (unsigned)tid;
-                        const unsigned i = ((t >> lj) << (lj + 1)) | (t & (j - 1u));
-                        const unsigned q = i + j;
-                        const unsigned long long a = batch[i], c = batch[q];
-                        const bool desc = ((i & k2) == 0);
-                        if (desc ? (a < c) : (a > c)) { batch[i] = c; batch[q] = a; }
-                    }
-                    __syncthreads();
-                }
-                if (warp_on) {
-                    if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
-                    reg_stages(k2, 32u);
-                    if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
-                }
-                __syncthreads();
-            }
-        }
+        sort_batch(nb);
         // ---- greedy acceptance, in rounds.  Round: (1) the next SEL_WIN words (32 candidates each) of the sorted
         // batch are tested against the accepted-corner grid, one warp per word (a candidate that fails is dead
         // for good: the accepted set only grows); (2) warp 0 takes the first 32 survivors of that window IN
