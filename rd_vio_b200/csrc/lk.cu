@@ -114,13 +114,6 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
         : "memory");
 }
 
-// 1-D bulk copy global -> shared, completing on an mbarrier (UBLKCP in SASS)
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // exact warp sum of int32 partials (|v| < 2^31): split so neither REDUX can overflow
 __device__ __forceinline__ long long warp_sum_exact(int v) {
     const int hi = v >> 16;
@@ -184,15 +177,10 @@ __device__ __forceinline__ int sample(const Pairs &t, const Pairs &b, unsigned w
 template <int WIN>
 struct __align__(128) WarpSmem {
     using C = LKCfg<WIN>;
-    // ipatch and dpatch are contiguous: a point whose templates come from the cache never stages these patches and uses
-    // the same bytes as the landing buffer of its packed template record (one level at a time, cp.async.bulk)
     uint8_t ipatch[(C::JW * C::IH + 127) / 128 * 128];
-    uint32_t dpatch[(C::DW * C::DH + 32 + 31) / 32 * 32];
     uint8_t jreg[C::JW * C::JH + 128];
-    uint64_t bar;            // TMA tile loads (I, dI, J)
-    uint64_t bar_tpl;        // bulk copies of cached template records
-    static constexpr int kRecordBytes = ((WIN * C::NSEG + 31) / 32) * 3 * 32 * 16;
-    static_assert(sizeof(ipatch) + sizeof(dpatch) >= (size_t)kRecordBytes, "template record must fit the I + dI patch area");
+    uint32_t dpatch[C::DW * C::DH + 32];
+    uint64_t bar;
 };
 
 // cvRound of a float in [0, 2^22): adding 1.5 * 2^23 rounds to nearest-even in the FADD itself (same result as
@@ -210,11 +198,11 @@ __device__ __forceinline__ void q14_weights(float a, float b, int &iw00, int &iw
 //   words [SEG, SEG + (SEG+1)/2): Ival of pixels 2q, 2q+1 as unsigned halves (0 <= Ival <= 8160)
 // One pyramidal LK pass A -> B for the warp's point.  (prevx, prevy): position in A (level 0);
 // (qx, qy): initial guess in / result out.  Returns the OpenCV status flag.
-// tc_ld / tcA_ld: cached templates of this point in A, valid at EVERY level (null: build them); tc_st / tcA_st: where
-// to store the templates built here (null: do not store).
+// tc_ld / tcA_ld: cached templates of this point in A (null: build them); tc_st / tcA_st: where to store the
+// templates built here (null: do not store).
 template <int WIN>
-__device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, uint32_t &phase_tpl, const LKMaps &maps, const LKParams &P,
-                                          int slotA, int slotB, float prevx, float prevy, float &qx, float &qy, const uint4 *tc_ld,
+__device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, const LKMaps &maps, const LKParams &P, int slotA, int slotB,
+                                          float prevx, float prevy, float &qx, float &qy, const uint4 *tc_ld,
                                           const float4 *tcA_ld, uint4 *tc_st, float4 *tcA_st) {
     using C = LKCfg<WIN>;
     constexpr int SEG = C::SEG, NSEG = C::NSEG, JW = C::JW, JH = C::JH, DW = C::DW;
@@ -237,14 +225,6 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, ui
         iseg[r] = tt - irow[r] * NSEG;
     }
 
-    constexpr uint32_t REC = WarpSmem<WIN>::kRecordBytes;      // packed template record of one level
-    if (tc_ld) {                                             // all levels of this point are cached: start with the top one
-        __syncwarp();
-        if (lane == 0) {
-            mbar_expect_tx(&ws.bar_tpl, REC);
-            bulk_load(ws.ipatch, tc_ld + (size_t)(P.nlevels - 1) * (REC / 16), REC, &ws.bar_tpl);
-        }
-    }
 #pragma unroll 1
     for (int level = P.nlevels - 1; level >= 0; --level) {
         const int cols = P.lw[level], rows = P.lh[level];
@@ -258,23 +238,16 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, ui
         if (tcA_st && lane == 0) tcA_st[level] = make_float4(0.f, 0.f, 0.f, 0.f);     // no template of this level (yet)
         px -= half; py -= half;
         const int ipx = (int)floorf(px), ipy = (int)floorf(py);
-        const bool cached = tc_ld != nullptr;            // warp-uniform; the kernel verified that every level is valid
         if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows) {
             if (level == 0) status = 0;
-            if (cached) {                                // (cannot happen for a record that exists; keep the copy pipeline consistent)
-                mbar_wait(&ws.bar_tpl, phase_tpl);
-                phase_tpl ^= 1u;
-                __syncwarp();
-                if (level > 0 && lane == 0) {
-                    mbar_expect_tx(&ws.bar_tpl, REC);
-                    bulk_load(ws.ipatch, tc_ld + (size_t)(level - 1) * (REC / 16), REC, &ws.bar_tpl);
-                }
-            }
             continue;
         }
+        // a cached template of this level?  (warp-uniform: every lane reads the same record)
         float A11 = 0.f, A12 = 0.f, A22 = 0.f;
-        if (cached) {
+        bool cached = false;
+        if (tcA_ld) {
             const float4 a = __ldg(tcA_ld + level);
+            cached = __float_as_uint(a.w) == 1u;
             A11 = a.x; A12 = a.y; A22 = a.z;
         }
         // ---- stage the J search region, and (if the template must be built) the I and dI patches (16-B aligned box starts)
@@ -304,17 +277,14 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, ui
         int Ixv[ROUNDS][SEG];                            // PACKED: (Iy << 16) | (Ix & 0xffff)
         int Iyv[C::PACKED ? 1 : ROUNDS][C::PACKED ? 1 : SEG];
         if (cached) {
-            // the record of this level was copied into the (otherwise unused) I / dI patch area while the previous
-            // level iterated: 3 conflict-free 16-byte shared loads per round
-            mbar_wait(&ws.bar_tpl, phase_tpl);
-            phase_tpl ^= 1u;
-            const uint4 *src = reinterpret_cast<const uint4 *>(ws.ipatch) + lane;
+            // 3 coalesced 16-byte loads per round while the J box is in flight
+            const uint4 *src = tc_ld + (size_t)level * (ROUNDS * 3 * 32) + lane;
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) {
                 unsigned w[12];
 #pragma unroll
                 for (int m = 0; m < 3; ++m) {
-                    const uint4 v = src[(r * 3 + m) * 32];
+                    const uint4 v = __ldg(src + (r * 3 + m) * 32);
                     w[4 * m] = v.x; w[4 * m + 1] = v.y; w[4 * m + 2] = v.z; w[4 * m + 3] = v.w;
                 }
 #pragma unroll
@@ -325,11 +295,6 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, ui
                     if constexpr (C::PACKED) Ixv[r][k] = (int)w[k];
                     else { Ixv[r][k] = (int)(short)(w[k] & 0xFFFFu); Iyv[r][k] = (int)w[k] >> 16; }
                 }
-            }
-            __syncwarp();                                // every lane has its words: the buffer may be refilled
-            if (level > 0 && lane == 0) {                // next level's record streams in while this level iterates
-                mbar_expect_tx(&ws.bar_tpl, REC);
-                bulk_load(ws.ipatch, tc_ld + (size_t)(level - 1) * (REC / 16), REC, &ws.bar_tpl);
             }
             mbar_wait(&ws.bar, phase);
             phase ^= 1u;
@@ -501,11 +466,10 @@ lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKP
     WarpSmem<WIN> &ws = smem[warp];
     if (lane == 0) {
         mbar_init(&ws.bar, 1);
-        mbar_init(&ws.bar_tpl, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    uint32_t phase = 0, phase_tpl = 0;
+    uint32_t phase = 0;
     const size_t idx = (size_t)b * P.stride + i;
     const float cx = (float)curr_xy[2 * idx], cy = (float)curr_xy[2 * idx + 1];
     float qx = cx, qy = cy;
@@ -534,19 +498,14 @@ lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKP
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m) found = base + __ffs(m) - 1;
         }
-        if (found >= 0) {
-            // usable only if the backward pass left a template at EVERY level (it skips a level that is out of the image or
-            // fails the min-eigenvalue test; then this pass rebuilds everything, which reproduces the same decisions)
-            const size_t e = (size_t)slotA * tc.max_points + found;
-            const bool ok = lane >= tc.levels || __float_as_uint(__ldg(tc.A + e * tc.levels + lane).w) == 1u;
-            if (__all_sync(0xffffffffu, ok)) {
-                tc_ld = tc.data + e * rec;
-                tcA_ld = tc.A + e * tc.levels;
-            } else found = -1;
-        }
         if (lane == 0) {
             atomicAdd(tc.stats, 1ull);
             if (found >= 0) atomicAdd(tc.stats + 1, 1ull);
+        }
+        if (found >= 0) {
+            const size_t e = (size_t)slotA * tc.max_points + found;
+            tc_ld = tc.data + e * rec;
+            tcA_ld = tc.A + e * tc.levels;
         }
     }
 
@@ -558,7 +517,7 @@ lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKP
         const int sA = dir ? slotB : slotA, sB = dir ? slotA : slotB;
         const float fromx = dir ? qx : cx, fromy = dir ? qy : cy;
         float gx = dir ? cx : qx, gy = dir ? cy : qy;
-        const int rst = lk_pyramid<WIN>(ws, phase, phase_tpl, maps, P, sA, sB, fromx, fromy, gx, gy, dir ? nullptr : tc_ld, dir ? nullptr : tcA_ld,
+        const int rst = lk_pyramid<WIN>(ws, phase, maps, P, sA, sB, fromx, fromy, gx, gy, dir ? nullptr : tc_ld, dir ? nullptr : tcA_ld,
                                         dir ? tc_st : nullptr, dir ? tcA_st : nullptr);
         if (dir == 0) {
             st = rst;

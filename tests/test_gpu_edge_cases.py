@@ -145,3 +145,20 @@ def test_random_odd_shapes_preprocess_bit_exact(orc):
                 assert np.array_equal(f.download_level(s, l, 2), np.pad(P.image(l), 21, mode="reflect")), (H, W, l)
             R = f.harris_response(s)
             assert np.array_equal(R, orc.harris(ref)), (H, W)
+
+
+def test_contexts_on_two_devices(orc):
+    """The > 48 KB dynamic shared memory opt-in is a per-device function attribute: a second context on another GPU of the
+    same process must get its own (round-1 bug: a process-wide cache skipped it).  1080p selection needs ~133 KB."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from rd_vio_b200.frontend import FrontEnd
+    img = random_image(1080, 1920, 77)
+    ref = orc.detect_keypoints(orc.clahe(img), np.zeros((0, 2)), 400, 20.0)[0]
+    for dev in (0, 1):
+        with FrontEnd(1920, 1080, max_level=3, win=21, num_slots=2, max_points=1024, device=dev) as f:
+            s = f.acquire()
+            f.preprocess([s], [img])
+            got = f.detect([s], [np.zeros((0, 2))], 400, 20.0)[0]
+            assert np.array_equal(got, ref), f"device {dev}"
