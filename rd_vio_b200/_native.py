@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librdvio_fe.so")
+# RDFE_LIB_PATH: an alternative build of the same library (kernel A/B experiments, scripts/lk_variants.sh); never a fallback
+LIB_PATH = os.environ.get("RDFE_LIB_PATH") or os.path.join(_HERE, "lib", "librdvio_fe.so")
 
 RDFE_MAX_BATCH = 128
 RDFE_MAX_LEVELS = 8

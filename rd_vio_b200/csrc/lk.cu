@@ -185,7 +185,11 @@ struct __align__(128) WarpSmem {
 
 // cvRound of a float in [0, 2^22): adding 1.5 * 2^23 rounds to nearest-even in the FADD itself (same result as
 // cvt.rni), on the FMA/ALU pipes instead of a quarter-rate F2I
+#ifdef LK_F2I
+__device__ __forceinline__ int rint_small(float v) { return __float2int_rn(v); }
+#else
 __device__ __forceinline__ int rint_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000; }
+#endif
 __device__ __forceinline__ void q14_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11) {
     iw00 = rint_small((1.f - a) * (1.f - b) * 16384.f);
     iw01 = rint_small(a * (1.f - b) * 16384.f);
@@ -368,7 +372,9 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, co
         float pdx = 0.f, pdy = 0.f;
         int cinx = INT_MIN, ciny = INT_MIN;              // integer origin the cached J words belong to
         Pairs Jt[ROUNDS], Jb[ROUNDS];
+#ifndef LK_NO_UNROLL1
 #pragma unroll 1
+#endif
         for (int j = 0; j < P.max_count; ++j) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
@@ -429,8 +435,14 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, co
             {
                 const float s2 = dx * dx + dy * dy;
                 bool conv;
+#ifdef LK_DOUBLE_CHECK
+                if (false) conv = false;
+#else
                 if (s2 > P.eps2_hi) conv = false;
+#endif
+#ifndef LK_DOUBLE_CHECK
                 else if (s2 < P.eps2_lo) conv = true;
+#endif
                 else conv = (double)dx * (double)dx + (double)dy * (double)dy <= P.eps2;
                 if (conv) break;
             }
