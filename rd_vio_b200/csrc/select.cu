@@ -612,6 +612,147 @@ poisson_append_kernel(SelectParams sp, const float *__restrict__ gftt_xy, const 
     if (lane == 0) kp_counts[b] = nout;
 }
 
+// ---- the same filter with the reference's own data structure: a cell grid holding ONE point index per cell (the last
+// one written, poisson_disk_filter.h:23-27,43-45), kept dense in shared memory over the cells a corner inside the image
+// can ever look at (test_point's 5x5 block minus its first cell plus one, :69-92).  A preset outside that range shares
+// no cell with an in-range one and is farther than the radius from every candidate, so it is simply not entered.
+// O(25) cell probes per candidate instead of the pairwise loops above; used whenever the grid fits shared memory.
+struct PoissonGrid {
+    int gw, gh;              // dense cells per axis (corner cells 0 .. gcw-1 shifted by OX = 2, OY = 2)
+};
+
+__global__ void __launch_bounds__(PO_THREADS)
+poisson_grid_kernel(SelectParams sp, PoissonGrid pg, const float *__restrict__ gftt_xy, const int *__restrict__ gftt_counts,
+                    double *__restrict__ kp_xy, int *__restrict__ kp_counts, const char *__restrict__ lk_status,
+                    unsigned *__restrict__ truncated) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *pxs = reinterpret_cast<double *>(smem_raw);                                     // [stride] preset x
+    double *pys = pxs + sp.stride;                                                          // [stride] preset y
+    float *ax = reinterpret_cast<float *>(pys + sp.stride);                                 // [cap_k] candidates
+    float *ay = ax + sp.cap_k;
+    int *grid = reinterpret_cast<int *>(ay + sp.cap_k);                                     // [gw*gh] point index or -1
+    unsigned char *pflag = reinterpret_cast<unsigned char *>(grid + pg.gw * pg.gh);         // [stride] status flags
+    unsigned char *cflag = pflag + sp.stride;                                               // [cap_k] candidate rejected
+    __shared__ int s_ne;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const int na = min(gftt_counts[b], sp.cap_k);
+    double *pts = kp_xy + (size_t)b * sp.stride * 2;
+    int ne = min(kp_counts[b], sp.stride);
+    const double radius = sp.kp_radius, r2 = radius * radius;
+    const double gsz = radius / sqrt(2.0);
+    constexpr int span = 2, OX = 2, OY = 2;                 // ceil(sqrt(2)) = 2
+    for (int i = tid; i < pg.gw * pg.gh; i += PO_THREADS) grid[i] = -1;
+    for (int i = tid; i < ne; i += PO_THREADS) {
+        pxs[i] = pts[2 * i]; pys[i] = pts[2 * i + 1];
+        pflag[i] = lk_status ? (lk_status[(size_t)b * sp.stride + i] != 0) : 1;
+    }
+    for (int c = tid; c < na; c += PO_THREADS) {
+        ax[c] = gftt_xy[((size_t)b * sp.cap_k + c) * 2];
+        ay[c] = gftt_xy[((size_t)b * sp.cap_k + c) * 2 + 1];
+    }
+    __syncthreads();
+    if (lk_status) {
+        // Frame::track_keypoints appends only the status != 0 points to the next frame, in order (frame.cpp:160-170)
+        if (warp == 0) {
+            int w = 0;
+            for (int base = 0; base < ne; base += 32) {
+                const int i = base + lane;
+                const bool keep = i < ne && pflag[i];
+                const double x = i < ne ? pxs[i] : 0.0, y = i < ne ? pys[i] : 0.0;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int pos = w + __popc(m & ((1u << lane) - 1u));
+                __syncwarp();
+                if (keep) { pxs[pos] = x; pys[pos] = y; }
+                w += __popc(m);
+            }
+            if (lane == 0) s_ne = w;
+        }
+        __syncthreads();
+        ne = s_ne;
+        for (int i = tid; i < ne; i += PO_THREADS) { pts[2 * i] = pxs[i]; pts[2 * i + 1] = pys[i]; }
+    }
+    // ---- preset_point in index order: the highest index written to a cell is the one that stays
+    for (int i = tid; i < ne; i += PO_THREADS) {
+        const int cx = (int)floor(pxs[i] / gsz) + OX, cy = (int)floor(pys[i] / gsz) + OY;
+        if (cx >= 0 && cx < pg.gw && cy >= 0 && cy < pg.gh) atomicMax(&grid[cy * pg.gw + cx], i);
+    }
+    __syncthreads();
+    // the 25 cells test_point visits, relative to the query cell: (dx, dy) in [-2, 2]^2 without (-2, -2), plus (-2, 3)
+    auto cell_of = [&](int q, int &dx, int &dy) {
+        if (q < 24) { const int t = q + 1; dx = t % 5 - span; dy = t / 5 - span; }
+        else { dx = -span; dy = span + 1; }
+    };
+    // ---- candidates against the presets: one thread per candidate
+    for (int c = tid; c < na; c += PO_THREADS) {
+        const double cx = (double)ax[c], cy = (double)ay[c];
+        const int ccx = (int)floor(cx / gsz) + OX, ccy = (int)floor(cy / gsz) + OY;
+        bool hit = false;
+        for (int q = 0; q < 25; ++q) {
+            int dx, dy;
+            cell_of(q, dx, dy);
+            const int i = grid[(ccy + dy) * pg.gw + (ccx + dx)];
+            if (i >= 0) {
+                const double ex = cx - pxs[i], ey = cy - pys[i];
+                if (ex * ex + ey * ey < r2) hit = true;
+            }
+        }
+        cflag[c] = hit ? 1 : 0;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    int nout = ne;              // write cursor in pts
+    if (sp.kp_radius * sp.kp_radius <= (double)sp.min_dist2 && sp.use_min_dist) {
+        // GFTT keeps its corners >= minDistance apart, so two NEW points never block each other, and a new point can
+        // only land in the cell of a preset it is closer than the radius to (cell diagonal = radius), i.e. never next to a
+        // visible one: the flags above are final -> parallel compaction.
+        for (int base = 0; base < na; base += 32) {
+            const int c = base + lane;
+            bool keep = false;
+            double cx = 0, cy = 0;
+            if (c < na && !cflag[c]) {
+                cx = (double)ax[c]; cy = (double)ay[c];
+                keep = !(cx < sp.border || cy < sp.border || cx >= sp.W - sp.border || cy >= sp.H - sp.border);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const int pos = nout + __popc(m & ((1u << lane) - 1u));
+            if (keep && pos < sp.stride) { pts[2 * pos] = cx; pts[2 * pos + 1] = cy; }
+            if (nout + __popc(m) > sp.stride && lane == 0) atomicOr(truncated, 2u);   // the reference's vector is unbounded
+            nout = min(nout + __popc(m), sp.stride);
+        }
+    } else {
+        // general radius: insertion in order; an accepted corner takes over its cell (index stride + c) and blocks later
+        // candidates.  Lane q probes cell q of the 25; presets need no second look (see above).
+        for (int c = 0; c < na; ++c) {
+            if (cflag[c]) continue;                      // warp-uniform (shared memory flag)
+            const double cx = (double)ax[c], cy = (double)ay[c];
+            const int ccx = (int)floor(cx / gsz) + OX, ccy = (int)floor(cy / gsz) + OY;
+            bool hit = false;
+            if (lane < 25) {
+                int dx, dy;
+                cell_of(lane, dx, dy);
+                const int i = grid[(ccy + dy) * pg.gw + (ccx + dx)];
+                if (i >= sp.stride) {
+                    const double ex = cx - (double)ax[i - sp.stride], ey = cy - (double)ay[i - sp.stride];
+                    if (ex * ex + ey * ey < r2) hit = true;
+                }
+            }
+            if (__any_sync(0xffffffffu, hit)) continue;
+            __syncwarp();
+            if (lane == 0) grid[ccy * pg.gw + ccx] = sp.stride + c;
+            __syncwarp();
+            const bool out_of_border = cx < sp.border || cy < sp.border || cx >= sp.W - sp.border || cy >= sp.H - sp.border;
+            if (!out_of_border) {
+                if (nout < sp.stride) {
+                    if (lane == 0) { pts[2 * nout] = cx; pts[2 * nout + 1] = cy; }
+                    ++nout;
+                } else if (lane == 0) atomicOr(truncated, 2u);
+            }
+        }
+    }
+    if (lane == 0) kp_counts[b] = nout;
+}
+
 static void fill_select_params(rdfe_ctx *ctx, const rdfe_detect_params &p, int stride, SelectParams &sp) {
     const LevelGeom &g = ctx->pyr.lv[0];
     sp.W = g.w; sp.H = g.h;
@@ -659,6 +800,27 @@ int launch_poisson_append(rdfe_ctx *ctx, int n, const rdfe_detect_params &p, con
                           const int *d_gftt_counts, double *d_xy, int *d_counts, int stride, const char *d_lk_status) {
     SelectParams sp;
     fill_select_params(ctx, p, stride, sp);
+    // dense cell grid (the reference's sparse_grid restricted to the cells a corner inside the image can probe)
+    static const int s_impl = [] { const char *e = getenv("RDFE_POISSON_IMPL"); return e ? atoi(e) : 1; }();
+    if (s_impl == 1 && p.keypoint_distance > 0.0) {
+        const double gsz = p.keypoint_distance / sqrt(2.0);
+        PoissonGrid pg;
+        pg.gw = (int)floor((double)(sp.W - 1) / gsz) + 1 + 4;       // corner cells + 2 on either side
+        pg.gh = (int)floor((double)(sp.H - 1) / gsz) + 1 + 5;       // ... and the extra probe at dy = +3
+        const size_t smem_g = (size_t)stride * 17 + (size_t)sp.cap_k * 9 + (size_t)pg.gw * pg.gh * 4 + 64;
+        if (smem_g <= 160 * 1024) {
+            if (smem_g > 48 * 1024 && smem_g > ctx->smem_optin[3]) {
+                if (cudaFuncSetAttribute(poisson_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g) != cudaSuccess) {
+                    set_error("poisson: cudaFuncSetAttribute(%zu) failed", smem_g);
+                    return RDFE_ERR_CUDA;
+                }
+                ctx->smem_optin[3] = smem_g;
+            }
+            RDFE_LAUNCH(ctx, K_POISSON, (poisson_grid_kernel<<<n, PO_THREADS, smem_g, ctx->ls>>>(sp, pg, d_gftt_xy, d_gftt_counts, d_xy, d_counts,
+                                                                                               d_lk_status, ctx->det.overflow)));
+            return 1;
+        }
+    }
     const size_t smem = (size_t)sp.cap_k * 21 + (size_t)stride * 25 + 64;
     if (smem > 200 * 1024) { set_error("poisson: shared memory need %zu B too large", smem); return RDFE_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024 && smem > ctx->smem_optin[1]) {
