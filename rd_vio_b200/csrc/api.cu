@@ -333,6 +333,9 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaMalloc(&ctx->det2.frame_max, RDFE_MAX_BATCH * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->det2.flag_count, RDFE_MAX_BATCH * sizeof(unsigned)));
     const size_t npts = (size_t)RDFE_MAX_BATCH * cfg->max_points;
+    ctx->io_bytes = mb * cfg->max_points * 33 + (size_t)RDFE_MAX_BATCH * 16 + 256;
+    CK(cudaMallocHost(&ctx->h_io, ctx->io_bytes));
+    CK(cudaMalloc(&ctx->d_io, ctx->io_bytes));
     CK(cudaMalloc(&ctx->d_xy_a, npts * 2 * sizeof(double)));
     CK(cudaMalloc(&ctx->d_xy_b, npts * 2 * sizeof(double)));
     CK(cudaMalloc(&ctx->d_counts, RDFE_MAX_BATCH * sizeof(int)));
@@ -465,6 +468,8 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->pf_done) cudaEventDestroy(ctx->pf_done);
     cudaFree(ctx->pf_gftt_xy); cudaFree(ctx->pf_gftt_resp); cudaFree(ctx->pf_gftt_counts);
     if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
+    if (ctx->h_io) cudaFreeHost(ctx->h_io);
+    cudaFree(ctx->d_io);
     free(ctx->slot_used);
     free(ctx->slot_gen);
     cudaFree(ctx->tc_data); cudaFree(ctx->tc_A); cudaFree(ctx->tc_hdr); cudaFree(ctx->tc_stats);
@@ -699,20 +704,26 @@ int rdfe_detect_batch(rdfe_ctx *ctx, const int *slots, int n, const rdfe_detect_
     for (int i = 0; i < n; ++i)
         if (counts[i] < 0 || counts[i] > stride) { set_error("rdfe_detect_batch: counts[%d]=%d out of range", i, counts[i]); return RDFE_ERR_INVALID; }
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
-    const size_t xyb = (size_t)n * stride * 2 * sizeof(double);
-    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_xy_a, keypoints_xy, xyb, cudaMemcpyHostToDevice, ctx->stream));
-    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_counts, counts, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = rdfe_detect_batch_dev(ctx, slots, n, p, ctx->d_xy_a, ctx->d_counts, stride, gftt_xy ? ctx->d_gftt_xy : nullptr,
+    if (n > ctx->max_batch) { set_error("rdfe_detect_batch: batch %d exceeds the context's %d slots", n, ctx->max_batch); return RDFE_ERR_INVALID; }
+    // pinned block [xy | counts]: one copy up, one copy back
+    const size_t xyb = (size_t)n * stride * 2 * sizeof(double), iob = xyb + (size_t)n * sizeof(int);
+    memcpy(ctx->h_io, keypoints_xy, xyb);
+    memcpy(ctx->h_io + xyb, counts, (size_t)n * sizeof(int));
+    double *d_xy = reinterpret_cast<double *>(ctx->d_io);
+    int *d_cnt = reinterpret_cast<int *>(ctx->d_io + xyb);
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_io, ctx->h_io, iob, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = rdfe_detect_batch_dev(ctx, slots, n, p, d_xy, d_cnt, stride, gftt_xy ? ctx->d_gftt_xy : nullptr,
                                    gftt_resp ? ctx->d_gftt_resp : nullptr, gftt_counts ? ctx->d_gftt_counts : nullptr);
     if (rc) return rc;
-    RDFE_CUDA_OK(cudaMemcpyAsync(keypoints_xy, ctx->d_xy_a, xyb, cudaMemcpyDeviceToHost, ctx->stream));
-    RDFE_CUDA_OK(cudaMemcpyAsync(counts, ctx->d_counts, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->h_io, ctx->d_io, iob, cudaMemcpyDeviceToHost, ctx->stream));
     const size_t k = (size_t)p->max_points;
     if (gftt_xy) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_xy, ctx->d_gftt_xy, n * k * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (gftt_resp) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_resp, ctx->d_gftt_resp, n * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (gftt_counts) RDFE_CUDA_OK(cudaMemcpyAsync(gftt_counts, ctx->d_gftt_counts, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RDFE_CUDA_OK(cudaMemcpyAsync(ctx->h_overflow, ctx->det.overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // everything this call launched is ordered on the main stream
+    memcpy(keypoints_xy, ctx->h_io, xyb);
+    memcpy(counts, ctx->h_io + xyb, (size_t)n * sizeof(int));
     if (*ctx->h_overflow) {
         cudaMemsetAsync(ctx->det.overflow, 0, sizeof(unsigned), ctx->stream);
         return report_overflow(ctx, *ctx->h_overflow);
@@ -746,22 +757,30 @@ int rdfe_track_batch(rdfe_ctx *ctx, const int *curr_slots, const int *next_slots
     for (int i = 0; i < n; ++i)
         if (counts[i] < 0 || counts[i] > stride) { set_error("rdfe_track_batch: counts[%d]=%d out of range", i, counts[i]); return RDFE_ERR_INVALID; }
     RDFE_CUDA_OK(cudaSetDevice(ctx->cfg.device));
-    const size_t xyb = (size_t)n * stride * 2 * sizeof(double);
-    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_xy_a, curr_xy, xyb, cudaMemcpyHostToDevice, ctx->stream));
-    if (p->has_prediction) RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_xy_b, next_xy, xyb, cudaMemcpyHostToDevice, ctx->stream));
-    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_counts, counts, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    RDFE_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, (size_t)n * stride, ctx->stream));
-    int rc = rdfe_track_batch_dev(ctx, curr_slots, next_slots, n, p, ctx->d_xy_a, ctx->d_xy_b, ctx->d_counts, stride, ctx->d_status);
+    if (n > ctx->max_batch) { set_error("rdfe_track_batch: batch %d exceeds the context's %d slots", n, ctx->max_batch); return RDFE_ERR_INVALID; }
+    // pinned block [curr | counts | next | status]: [curr | counts (| next = prediction)] goes up in one copy,
+    // [next | status] comes back in one copy.  LK writes the status of every point below counts[i]; entries beyond are 0.
+    const size_t xyb = (size_t)n * stride * 2 * sizeof(double), cb = ((size_t)n * sizeof(int) + 15) & ~(size_t)15;
+    const size_t off_cnt = xyb, off_next = xyb + cb, off_st = off_next + xyb, stb = (size_t)n * stride;
+    memcpy(ctx->h_io, curr_xy, xyb);
+    memcpy(ctx->h_io + off_cnt, counts, (size_t)n * sizeof(int));
+    if (p->has_prediction) memcpy(ctx->h_io + off_next, next_xy, xyb);
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->d_io, ctx->h_io, p->has_prediction ? off_st : off_next, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = rdfe_track_batch_dev(ctx, curr_slots, next_slots, n, p, reinterpret_cast<const double *>(ctx->d_io),
+                                  reinterpret_cast<double *>(ctx->d_io + off_next), reinterpret_cast<const int *>(ctx->d_io + off_cnt), stride,
+                                  reinterpret_cast<char *>(ctx->d_io + off_st));
     if (rc) return rc;
+    RDFE_CUDA_OK(cudaMemcpyAsync(ctx->h_io + off_next, ctx->d_io + off_next, xyb + stb, cudaMemcpyDeviceToHost, ctx->stream));
+    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // the LK launch and the copy back are ordered on the main stream
     // only status != 0 entries of next_xy may change (opencv_image.cpp:148-153): merge on the host
-    std::vector<double> tmp((size_t)n * stride * 2);
-    RDFE_CUDA_OK(cudaMemcpyAsync(tmp.data(), ctx->d_xy_b, xyb, cudaMemcpyDeviceToHost, ctx->stream));
-    RDFE_CUDA_OK(cudaMemcpyAsync(status, ctx->d_status, (size_t)n * stride, cudaMemcpyDeviceToHost, ctx->stream));
-    RDFE_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // the LK launch and these copies are ordered on the main stream
+    const double *hn = reinterpret_cast<const double *>(ctx->h_io + off_next);
+    const char *hst = reinterpret_cast<const char *>(ctx->h_io + off_st);
+    memset(status, 0, stb);
     for (int b = 0; b < n; ++b)
         for (int i = 0; i < counts[b]; ++i) {
             const size_t k = (size_t)b * stride + i;
-            if (status[k]) { next_xy[2 * k] = tmp[2 * k]; next_xy[2 * k + 1] = tmp[2 * k + 1]; }
+            status[k] = hst[k];
+            if (hst[k]) { next_xy[2 * k] = hn[2 * k]; next_xy[2 * k + 1] = hn[2 * k + 1]; }
         }
     return RDFE_OK;
 }

@@ -246,6 +246,10 @@ struct rdfe_ctx {
     // scratch
     uint8_t *lut;                 // [RDFE_MAX_BATCH][tiles][256]
     rdfe::DetectScratch det;
+    // host-pointer track / detect: ONE pinned block and its device twin, so that a call is one H2D, the kernels, one D2H
+    // (copies straight from / to the caller's pageable vectors cost a staged driver copy each)
+    uint8_t *h_io, *d_io;
+    size_t io_bytes;
     // host<->device staging for the host-pointer API
     double *d_xy_a, *d_xy_b;      // [RDFE_MAX_BATCH][max_points][2]
     int *d_counts;                // [RDFE_MAX_BATCH]
