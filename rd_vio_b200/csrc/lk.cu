@@ -36,8 +36,11 @@
 namespace rdfe {
 
 template <int WIN> struct LKCfg;
+// MIN_CTAS = 5 caps the 21x21 kernel at 96 registers (a few spills in the template build): alone it is 3 % slower than at
+// 128 registers / 4 CTAs, but 20 warps per SM and smaller CTAs leave room beside the other streams' kernels:
+// +1.1 % frames/s in the pipelined step (A/B twice on one box: 178.9 k -> 180.9 k; 80 registers / 6 CTAs: 178.5 k)
 template <> struct LKCfg<21> {
-    static constexpr int SEG = 7, NSEG = 3, JW = 48, JH = 32, IH = 22, DW = 28, DH = 22, MARGIN = 5, WARPS = 4, MIN_CTAS = 4;
+    static constexpr int SEG = 7, NSEG = 3, JW = 48, JH = 32, IH = 22, DW = 28, DH = 22, MARGIN = 5, WARPS = 4, MIN_CTAS = 5;
     static constexpr bool PACKED = false;
 };
 template <> struct LKCfg<31> {
