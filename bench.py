@@ -535,7 +535,7 @@ def annotate_kernels(m, hbm_peak, peak_src, sm_mhz):
             v["achieved_gbs"] = (sb / (v["ms_per_step"] * 1e-3) / 1e9) if v["ms_per_step"] > 0 else 0.0
             v["hbm_frac"] = v["achieved_gbs"] / hbm_peak
             for cname, c in counters.items():
-                if cname.startswith(kname) and v["us_per_launch"] > 0:
+                if (cname.startswith(kname) or (kname == "poisson_append" and cname.startswith("poisson_"))) and v["us_per_launch"] > 0:
                     t_s = v["us_per_launch"] * 1e-6
                     if c.get("warp_inst_per_launch"):
                         # warp instructions / (4 schedulers x 148 SMs x clock x time): 1.0 = every issue slot used
