@@ -1,8 +1,7 @@
-B="python bench.py --no-cpu-baseline --no-e2e --steps 200 --warmup 10 --profile-steps 0"
-i=0
-for P in "-1,0,0,0,0" "-2,-1,-1,0,0" "-1,0,-1,0,-1" "-1,-1,0,0,0" "-2,0,0,-1,-1"; do
-  RDFE_PRIO="$P" $B > gpurun_out/q$i.json 2>gpurun_out/q$i.err
-  python -c "
-import json; d=json.loads(open('gpurun_out/q$i.json').read().strip().splitlines()[-1]); print('prio $P', round(d['value']), d['ms_per_step'])"
-  i=$((i+1))
-done
+# stream priorities of the pipelined step (pre,harris,select,lk,poisson); round 2, after the register-footprint changes
+B="python bench.py --no-cpu-baseline --no-e2e --steps 200 --warmup 10 --profile-steps 0 --no-other-configs --no-chained"
+for rep in 1 2; do
+for P in "-1,0,0,0,-2" "-1,0,0,0,-1" "-1,0,0,0,-3" "-2,0,0,0,-3" "-2,0,0,0,-1" "-3,0,0,0,-5" "-1,0,0,0,-5" "-2,0,0,-1,-3" "-2,-1,0,-1,-3"; do
+  RDFE_PRIO="$P" timeout 120 $B 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('prio $P', round(d['value']), round(d['ms_per_step'],4))"
+done; done
