@@ -15,13 +15,15 @@ ap.add_argument("--stream", type=int, default=3)
 ap.add_argument("--frames", type=int, default=200)
 ap.add_argument("--pred", default="none")
 ap.add_argument("--skip", type=int, default=1, help="frame stride (larger = larger motion)")
+ap.add_argument("--cache", action="store_true", help="LK template cache on (must not change a single result)")
 a = ap.parse_args()
 wl = WORKLOADS[a.workload]
 W, H, NP, ML, WIN = wl["width"], wl["height"], wl["points"], wl["max_level"], wl["win"]
 st = SyntheticStream(a.stream, W, H, period=200)
 bad = 0
-tag = f"[{a.workload} s{a.stream} {a.pred} skip{a.skip}]"
+tag = f"[{a.workload} s{a.stream} {a.pred} skip{a.skip}{' cache' if a.cache else ''}]"
 with FrontEnd(W, H, ML, WIN, num_slots=4, max_points=4 * NP + 64) as fe:
+    fe.set_template_cache(a.cache)
     last_pyr, last_slot, last_kp = None, None, None
     for i in range(a.frames):
         f = st.frame(i * a.skip)
