@@ -164,58 +164,58 @@ select_kernel(DetectScratch det, SelectParams sp, Pyramid pyr, SlotList slots, f
 
         // Bitonic sort of batch[0, cnt) (descending), used for the pivot sample and for the batch itself.
         auto sort_batch = [&](unsigned cnt) {
-        unsigned N = 32;
-        while (N < cnt) N <<= 1;
-        for (unsigned i = cnt + tid; i < N; i += SEL_THREADS) batch[i] = 0ull;
-        __syncthreads();
-        // Bitonic sort, descending.  Thread t owns elements 2t and 2t+1 for the exchange distances j <= 32 (its
-        // partner for distance j is lane t ^ (j/2): register shuffles, no barrier); distances >= 64 go through
-        // shared memory.  All merges up to k2 = 64 stay inside one warp's 64 elements.
-        {
-            const unsigned half = N >> 1;
-            const bool warp_on = (unsigned)(warp * 32) < half;            // warp-uniform
-            const bool own = (unsigned)tid < half;
-            const unsigned e_idx = 2u * (unsigned)tid;
-            unsigned long long e0 = 0ull, e1 = 0ull;
-            auto reg_stages = [&](unsigned k2, unsigned jstart) {
-                const bool desc = (e_idx & k2) == 0;
-                for (unsigned j = jstart; j >= 2; j >>= 1) {
-                    const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, e0, (int)(j >> 1));
-                    const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, e1, (int)(j >> 1));
-                    const bool keep_max = ((e_idx & j) == 0) == desc;
-                    e0 = keep_max ? (e0 > p0 ? e0 : p0) : (e0 < p0 ? e0 : p0);
-                    e1 = keep_max ? (e1 > p1 ? e1 : p1) : (e1 < p1 ? e1 : p1);
-                }
-                const unsigned long long hi = e0 > e1 ? e0 : e1, lo = e0 > e1 ? e1 : e0;
-                e0 = desc ? hi : lo;
-                e1 = desc ? lo : hi;
-            };
-            if (warp_on) {
-                if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
-                for (unsigned k2 = 2; k2 <= min(N, 64u); k2 <<= 1) reg_stages(k2, k2 >> 1);
-                if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
-            }
+            unsigned N = 32;
+            while (N < cnt) N <<= 1;
+            for (unsigned i = cnt + tid; i < N; i += SEL_THREADS) batch[i] = 0ull;
             __syncthreads();
-            for (unsigned k2 = 128; k2 <= N; k2 <<= 1) {
-                for (unsigned j = k2 >> 1, lj = 31 - __clz(k2 >> 1); j >= 64; j >>= 1, --lj) {
-                    if (own) {
-                        const unsigned t = (unsigned)tid;
-                        const unsigned i = ((t >> lj) << (lj + 1)) | (t & (j - 1u));
-                        const unsigned q = i + j;
-                        const unsigned long long a = batch[i], c = batch[q];
-                        const bool desc = ((i & k2) == 0);
-                        if (desc ? (a < c) : (a > c)) { batch[i] = c; batch[q] = a; }
+            // Bitonic sort, descending.  Thread t owns elements 2t and 2t+1 for the exchange distances j <= 32 (its
+            // partner for distance j is lane t ^ (j/2): register shuffles, no barrier); distances >= 64 go through
+            // shared memory.  All merges up to k2 = 64 stay inside one warp's 64 elements.
+            {
+                const unsigned half = N >> 1;
+                const bool warp_on = (unsigned)(warp * 32) < half;            // warp-uniform
+                const bool own = (unsigned)tid < half;
+                const unsigned e_idx = 2u * (unsigned)tid;
+                unsigned long long e0 = 0ull, e1 = 0ull;
+                auto reg_stages = [&](unsigned k2, unsigned jstart) {
+                    const bool desc = (e_idx & k2) == 0;
+                    for (unsigned j = jstart; j >= 2; j >>= 1) {
+                        const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, e0, (int)(j >> 1));
+                        const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, e1, (int)(j >> 1));
+                        const bool keep_max = ((e_idx & j) == 0) == desc;
+                        e0 = keep_max ? (e0 > p0 ? e0 : p0) : (e0 < p0 ? e0 : p0);
+                        e1 = keep_max ? (e1 > p1 ? e1 : p1) : (e1 < p1 ? e1 : p1);
                     }
-                    __syncthreads();
-                }
+                    const unsigned long long hi = e0 > e1 ? e0 : e1, lo = e0 > e1 ? e1 : e0;
+                    e0 = desc ? hi : lo;
+                    e1 = desc ? lo : hi;
+                };
                 if (warp_on) {
                     if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
-                    reg_stages(k2, 32u);
+                    for (unsigned k2 = 2; k2 <= min(N, 64u); k2 <<= 1) reg_stages(k2, k2 >> 1);
                     if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
                 }
                 __syncthreads();
+                for (unsigned k2 = 128; k2 <= N; k2 <<= 1) {
+                    for (unsigned j = k2 >> 1, lj = 31 - __clz(k2 >> 1); j >= 64; j >>= 1, --lj) {
+                        if (own) {
+                            const unsigned t = (unsigned)tid;
+                            const unsigned i = ((t >> lj) << (lj + 1)) | (t & (j - 1u));
+                            const unsigned q = i + j;
+                            const unsigned long long a = batch[i], c = batch[q];
+                            const bool desc = ((i & k2) == 0);
+                            if (desc ? (a < c) : (a > c)) { batch[i] = c; batch[q] = a; }
+                        }
+                        __syncthreads();
+                    }
+                    if (warp_on) {
+                        if (own) { const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(batch)[tid]; e0 = v.x; e1 = v.y; }
+                        reg_stages(k2, 32u);
+                        if (own) reinterpret_cast<ulonglong2 *>(batch)[tid] = make_ulonglong2(e0, e1);
+                    }
+                    __syncthreads();
+                }
             }
-        }
         };
         // ---- pivot for the next batch.  ANY threshold lo gives an exact batch (the keys >= lo are a prefix of the
         // descending order) as long as at most SEL_CAP keys pass it, so the pivot comes from a sorted sample of <= SEL_CAP
@@ -260,86 +260,86 @@ select_kernel(DetectScratch det, SelectParams sp, Pyramid pyr, SlotList slots, f
             __syncthreads();
         }
         if (!gathered) {
-        // ---- exact radix select of the SEL_CAP-th largest eligible key (last resort, and the whole list when it fits)
-        if (n_el > SEL_CAP) {
-            if (tid == 0) { s_prefix = 0; s_k = SEL_CAP; }
-            unsigned long long mask = 0;
-            bool early = false;
-            for (int pass = 7; pass >= 0; --pass) {
-                if (pass < 4 && pass >= low_passes) continue;      // digits known to be zero
-                const int shift = pass * 8;
-                if (tid < 256) hist[tid] = 0;
-                __syncthreads();
-                const unsigned long long prefix = s_prefix;
-                // Equal digits are the norm in the high passes (responses share their exponent byte): when a whole
-                // warp agrees on the digit one lane adds the count, otherwise plain shared-memory atomics.
-                for (unsigned base = warp * 32; base < n; base += SEL_THREADS) {
-                    const unsigned i = base + lane;
-                    unsigned long long k = 0;
-                    bool part = false;
-                    if (i < n) { k = keys[i]; part = (k & mask) == prefix; }
-                    const unsigned d = (unsigned)(k >> shift) & 255u;
-                    // fast path: every participating lane holds the same digit (typical for the exponent bytes)
-                    const unsigned pm = __ballot_sync(0xffffffffu, part);
-                    if (pm) {
-                        const unsigned d0 = __shfl_sync(0xffffffffu, d, __ffs(pm) - 1);
-                        const bool same = __all_sync(0xffffffffu, !part || d == d0);
-                        if (same) { if (lane == __ffs(pm) - 1) atomicAdd(&hist[d0], (unsigned)__popc(pm)); }
-                        else if (part) atomicAdd(&hist[d], 1u);
-                    }
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    // lane l owns digits 255-8l .. 248-8l (descending)
-                    unsigned loc[8], tot = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { loc[j] = hist[255 - 8 * lane - j]; tot += loc[j]; }
-                    unsigned inc = tot;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-                        if (lane >= d) inc += t;
-                    }
-                    const unsigned kk = s_k;
-                    const unsigned ball = __ballot_sync(0xffffffffu, inc >= kk);
-                    const int owner = __ffs(ball) - 1;               // exists: total >= kk
-                    if (lane == owner) {
-                        unsigned cum = inc - tot;
-                        int dsel = 0;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (cum + loc[j] >= kk) { dsel = 255 - 8 * lane - j; break; }
-                            cum += loc[j];
+            // ---- exact radix select of the SEL_CAP-th largest eligible key (last resort, and the whole list when it fits)
+            if (n_el > SEL_CAP) {
+                if (tid == 0) { s_prefix = 0; s_k = SEL_CAP; }
+                unsigned long long mask = 0;
+                bool early = false;
+                for (int pass = 7; pass >= 0; --pass) {
+                    if (pass < 4 && pass >= low_passes) continue;      // digits known to be zero
+                    const int shift = pass * 8;
+                    if (tid < 256) hist[tid] = 0;
+                    __syncthreads();
+                    const unsigned long long prefix = s_prefix;
+                    // Equal digits are the norm in the high passes (responses share their exponent byte): when a whole
+                    // warp agrees on the digit one lane adds the count, otherwise plain shared-memory atomics.
+                    for (unsigned base = warp * 32; base < n; base += SEL_THREADS) {
+                        const unsigned i = base + lane;
+                        unsigned long long k = 0;
+                        bool part = false;
+                        if (i < n) { k = keys[i]; part = (k & mask) == prefix; }
+                        const unsigned d = (unsigned)(k >> shift) & 255u;
+                        // fast path: every participating lane holds the same digit (typical for the exponent bytes)
+                        const unsigned pm = __ballot_sync(0xffffffffu, part);
+                        if (pm) {
+                            const unsigned d0 = __shfl_sync(0xffffffffu, d, __ffs(pm) - 1);
+                            const bool same = __all_sync(0xffffffffu, !part || d == d0);
+                            if (same) { if (lane == __ffs(pm) - 1) atomicAdd(&hist[d0], (unsigned)__popc(pm)); }
+                            else if (part) atomicAdd(&hist[d], 1u);
                         }
-                        s_k = kk - cum;
-                        s_prefix = prefix | ((unsigned long long)dsel << shift);
                     }
+                    __syncthreads();
+                    if (warp == 0) {
+                        // lane l owns digits 255-8l .. 248-8l (descending)
+                        unsigned loc[8], tot = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { loc[j] = hist[255 - 8 * lane - j]; tot += loc[j]; }
+                        unsigned inc = tot;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+                            if (lane >= d) inc += t;
+                        }
+                        const unsigned kk = s_k;
+                        const unsigned ball = __ballot_sync(0xffffffffu, inc >= kk);
+                        const int owner = __ffs(ball) - 1;               // exists: total >= kk
+                        if (lane == owner) {
+                            unsigned cum = inc - tot;
+                            int dsel = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (cum + loc[j] >= kk) { dsel = 255 - 8 * lane - j; break; }
+                                cum += loc[j];
+                            }
+                            s_k = kk - cum;
+                            s_prefix = prefix | ((unsigned long long)dsel << shift);
+                        }
+                    }
+                    mask |= 255ull << shift;
+                    __syncthreads();
+                    // The response bits are settled after pass 4.  Any threshold gives an exact batch (a prefix of the
+                    // sorted order), so unless ties on the response leave the batch less than half full, take the
+                    // keys whose response is strictly larger and skip the address passes.
+                    if (pass == 4 && SEL_CAP - s_k >= SEL_CAP / 2) { early = true; break; }
                 }
-                mask |= 255ull << shift;
-                __syncthreads();
-                // The response bits are settled after pass 4.  Any threshold gives an exact batch (a prefix of the
-                // sorted order), so unless ties on the response leave the batch less than half full, take the
-                // keys whose response is strictly larger and skip the address passes.
-                if (pass == 4 && SEL_CAP - s_k >= SEL_CAP / 2) { early = true; break; }
+                lo = early ? s_prefix + (1ull << 32) : s_prefix;
             }
-            lo = early ? s_prefix + (1ull << 32) : s_prefix;
-        }
-        // ---- gather [lo, hi) and sort descending
-        if (tid == 0) s_nb = 0;
-        __syncthreads();
-        for (unsigned i0 = tid; i0 < n; i0 += 4 * SEL_THREADS) {
-            unsigned long long kq[4];
+            // ---- gather [lo, hi) and sort descending
+            if (tid == 0) s_nb = 0;
+            __syncthreads();
+            for (unsigned i0 = tid; i0 < n; i0 += 4 * SEL_THREADS) {
+                unsigned long long kq[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) kq[u] = (i0 + u * SEL_THREADS < n) ? keys[i0 + u * SEL_THREADS] : 0ull;
+                for (int u = 0; u < 4; ++u) kq[u] = (i0 + u * SEL_THREADS < n) ? keys[i0 + u * SEL_THREADS] : 0ull;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (kq[u] >= lo && kq[u] != 0ull) {
-                    const unsigned pos = atomicAdd(&s_nb, 1u);
-                    if (pos < SEL_CAP) batch[pos] = kq[u];
-                }
+                for (int u = 0; u < 4; ++u)
+                    if (kq[u] >= lo && kq[u] != 0ull) {
+                        const unsigned pos = atomicAdd(&s_nb, 1u);
+                        if (pos < SEL_CAP) batch[pos] = kq[u];
+                    }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        }   // !gathered
         const unsigned nb = min(s_nb, (unsigned)SEL_CAP);
         sort_batch(nb);
         // ---- greedy acceptance, in rounds.  Round: (1) the next SEL_WIN words (32 candidates each) of the sorted
