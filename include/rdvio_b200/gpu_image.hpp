@@ -63,10 +63,9 @@ class GpuFrontEnd {
             // preprocess() returns once the frame is uploaded: the image Mat outlives the copy (it is held until
             // release_image_buffer()), and track/detect are ordered behind the pyramid on the context's stream
             rdfe_set_host_sync(ctx, 0);
-            // Frame::track_keypoints re-projects the points it carried on (apply_k(remove_k(p)), frame.cpp:76-79), which
-            // returns the same float pixel: the templates the backward LK pass built there serve the next forward pass
-            // (8 slots x 4096 points x ~12 KB of HBM; a failure only means the cache stays off)
-            rdfe_set_template_cache(ctx, 1);
+            // The LK template cache (rdfe_set_template_cache) would apply here -- Frame::track_keypoints re-projects the points
+            // it carried on (apply_k(remove_k(p)), frame.cpp:76-79), which returns the same float pixel -- but it stays off:
+            // the kernel variant that carries the cache paths measured slower than the plain one.
         }
         ctxs[key] = ctx;
         return ctx;

@@ -465,7 +465,8 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, co
     return status;
 }
 
-template <int WIN, int CTAS>
+// CACHE = false compiles every template-cache path out (the launcher picks it whenever the cache is off)
+template <int WIN, int CTAS, bool CACHE>
 __global__ void __launch_bounds__(LKCfg<WIN>::WARPS * 32, CTAS)
 lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKParams P, const __grid_constant__ SlotList curr,
                 const __grid_constant__ SlotList next, const __grid_constant__ LKCache tc, const double *__restrict__ curr_xy,
@@ -499,7 +500,7 @@ lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKP
     uint4 *tc_st = nullptr;
     float4 *tcA_st = nullptr;
     const size_t rec = (size_t)tc.levels * (ROUNDS * 3 * 32);       // uint4 per point
-    if (tc.data) {
+    if (CACHE && tc.data) {
         const float4 *hdr = tc.hdr + (size_t)slotA * tc.max_points;
         const unsigned gen = tc.gen_curr[b];
         int found = -1;
@@ -532,8 +533,9 @@ lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKP
         const int sA = dir ? slotB : slotA, sB = dir ? slotA : slotB;
         const float fromx = dir ? qx : cx, fromy = dir ? qy : cy;
         float gx = dir ? cx : qx, gy = dir ? cy : qy;
-        const int rst = lk_pyramid<WIN>(ws, phase, maps, P, sA, sB, fromx, fromy, gx, gy, dir ? nullptr : tc_ld, dir ? nullptr : tcA_ld,
-                                        dir ? tc_st : nullptr, dir ? tcA_st : nullptr);
+        const int rst = lk_pyramid<WIN>(ws, phase, maps, P, sA, sB, fromx, fromy, gx, gy, (CACHE && !dir) ? tc_ld : nullptr,
+                                        (CACHE && !dir) ? tcA_ld : nullptr, (CACHE && dir) ? tc_st : nullptr,
+                                        (CACHE && dir) ? tcA_st : nullptr);
         if (dir == 0) {
             st = rst;
             qx = gx; qy = gy;
@@ -543,7 +545,7 @@ lk_track_kernel(const __grid_constant__ LKMaps maps, const __grid_constant__ LKP
                 if (sqrt((double)dx * (double)dx + (double)dy * (double)dy) > P.max_jump) st = 0;
             }
             if (!st) break;
-            if (tc.data && i < tc.max_points) {
+            if (CACHE && tc.data && i < tc.max_points) {
                 const size_t e = (size_t)slotB * tc.max_points + i;
                 tc_st = tc.data + e * rec;
                 tcA_st = tc.A + e * tc.levels;
@@ -600,12 +602,20 @@ int launch_lk(rdfe_ctx *ctx, const SlotList &curr, const SlotList &next, const r
     }
     if (pyr.win == 21) {
         dim3 grid((stride + LKCfg<21>::WARPS - 1) / LKCfg<21>::WARPS, curr.n);
-        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21, LKCfg<21>::MIN_CTAS><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->ls>>>(
-                                   maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
+        if (tc.data)
+            RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21, LKCfg<21>::MIN_CTAS, true><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->ls>>>(
+                                       maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
+        else
+            RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<21, LKCfg<21>::MIN_CTAS, false><<<grid, LKCfg<21>::WARPS * 32, 0, ctx->ls>>>(
+                                       maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
     } else if (pyr.win == 31) {
         dim3 grid((stride + LKCfg<31>::WARPS - 1) / LKCfg<31>::WARPS, curr.n);
-        RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31, LKCfg<31>::MIN_CTAS><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->ls>>>(
-                                   maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
+        if (tc.data)
+            RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31, LKCfg<31>::MIN_CTAS, true><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->ls>>>(
+                                       maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
+        else
+            RDFE_LAUNCH(ctx, K_LK, (lk_track_kernel<31, LKCfg<31>::MIN_CTAS, false><<<grid, LKCfg<31>::WARPS * 32, 0, ctx->ls>>>(
+                                       maps, P, curr, next, tc, d_curr_xy, d_next_xy, d_counts, d_status)));
     } else {
         set_error("LK window %d unsupported (21 or 31)", pyr.win);
         return RDFE_ERR_UNSUPPORTED;
