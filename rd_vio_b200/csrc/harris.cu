@@ -71,7 +71,7 @@ __device__ __forceinline__ double shfl_down_d(double v) {
 // stay warp-wide: what crosses a group boundary only reaches apron columns whose results are never used, exactly
 // like lanes 0 and 31 of the one-group case.  y0, the row count and every row predicate are then per lane; the loop
 // trip count, the staging flush and the REDUX stay warp-uniform (group 0 always has the most rows).
-template <bool kFma, bool BORDER>
+template <bool kFma, bool BORDER, bool RESP>
 __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, int ipitch, int W, int H, int x0, int y0w, int hr_rows, int gl_lanes,
                                              int n_groups, float k, const DetectScratch &det, int b, float *__restrict__ response,
                                              unsigned long long *buf, unsigned *cnt) {
@@ -135,7 +135,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
     unsigned wq0 = 0, wq1 = 0;
     if (ld_ok) { wq0 = *reinterpret_cast<const unsigned *>(rowp); wq1 = *reinterpret_cast<const unsigned *>(rowp + ipitch); }
     rowp += 2 * (ptrdiff_t)ipitch;
-    float *resp_row = response ? response + ((size_t)b * H + (y0 - 5)) * W + c0 : nullptr;   // row q = y0-5+j
+    float *resp_row = RESP ? response + ((size_t)b * H + (y0 - 5)) * W + c0 : nullptr;   // row q = y0-5+j (debug tap only)
     unsigned addr_row = (unsigned)((y0 - 6) * W + c0);       // pixel address of (row n = y0-6+j, column c0)
 #pragma unroll 2
     for (int j = 0; j < steps; ++j) {
@@ -206,7 +206,7 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
         }
         Rn[0] = __shfl_up_sync(0xffffffffu, Rn[4], 1);
         Rn[5] = __shfl_down_sync(0xffffffffu, Rn[1], 1);
-        if (response) {
+        if (RESP) {
             if (out_lane && q >= y0 && q < y0 + rows) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -254,7 +254,8 @@ __device__ __forceinline__ void harris_strip(const uint8_t *__restrict__ org, in
     if (lane == 0 && mb) atomicMax(&det.frame_max[b], mb);
 }
 
-template <bool kFma>
+// RESP = true only for the rdfe_harris_response debug tap: the hot path carries neither the pointer nor the branch
+template <bool kFma, bool RESP>
 __global__ void __launch_bounds__(HW_WARPS * 32)
 harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float *__restrict__ response, int tiles_x,
                   int strips, int gl_narrow, int n_items, int hr_rows) {
@@ -280,8 +281,8 @@ harris_nms_kernel(Pyramid pyr, SlotList slots, float k, DetectScratch det, float
         // interior strip: columns x0-5 .. x0+124 and rows y0-6 .. y0+hr_rows+2 all inside the image, and the
         // outputs stay off the 1-px frame
         const bool interior = (x0 - 5 >= 0) && (x0 + 124 < W) && (y0 - 6 >= 0) && (y0 + hr_rows + 2 < H);
-        if (interior) harris_strip<kFma, false>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, k, det, b, response, s_buf[warp], &s_cnt[warp]);
-        else harris_strip<kFma, true>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+        if (interior) harris_strip<kFma, false, RESP>(org, ipitch, W, H, x0, y0, hr_rows, 32, 1, k, det, b, response, s_buf[warp], &s_cnt[warp]);
+        else harris_strip<kFma, true, RESP>(org, ipitch, W, H, x0, y0, hr_rows, gl_lanes, n_groups, k, det, b, response, s_buf[warp], &s_cnt[warp]);
     }
 }
 
@@ -966,9 +967,15 @@ int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_de
         return 2;
     }
     if (p.harris_fma)
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        if (d_response)
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true, true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        else
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<true, false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, nullptr, tiles_x, strips, gl_narrow, n_items, hr_rows)));
     else
-        RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        if (d_response)
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false, true><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, d_response, tiles_x, strips, gl_narrow, n_items, hr_rows)));
+        else
+            RDFE_LAUNCH(ctx, K_HARRIS, (harris_nms_kernel<false, false><<<grid, HW_WARPS * 32, 0, ctx->ls>>>(ctx->pyr, slots, (float)p.harris_k, ctx->det, nullptr, tiles_x, strips, gl_narrow, n_items, hr_rows)));
     return 2;
 }
 

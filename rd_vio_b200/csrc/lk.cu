@@ -101,13 +101,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a TMA that never completes (bad descriptor) traps instead of hanging the GPU.
+// Bounded wait: a TMA that never completes (bad descriptor) traps instead of hanging the GPU (the launch then fails with
+// an error the host reports; no printf here: its argument set-up costs registers in the hot kernel).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 20)) {
-            if ((threadIdx.x & 31) == 0) printf("rdfe lk: TMA wait timed out (block %d,%d warp %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5, parity);
-            __trap();
-        }
+        if (spins > (1u << 20)) __trap();
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar) {
     asm volatile(
