@@ -224,7 +224,7 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, co
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
         const int t = lane + 32 * r;
-        ivalid[r] = t < ITEMS;
+        ivalid[r] = (32 * (r + 1) <= ITEMS) || t < ITEMS;     // only the last round can hold idle lanes (compile-time for the others)
         const int tt = ivalid[r] ? t : 0;
         irow[r] = tt / NSEG;
         iseg[r] = tt - irow[r] * NSEG;
@@ -233,7 +233,7 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, co
 #pragma unroll 1
     for (int level = P.nlevels - 1; level >= 0; --level) {
         const int cols = P.lw[level], rows = P.lh[level];
-        const float lscale = (float)(1. / (double)(1 << level));
+        const float lscale = __int_as_float((127 - level) << 23);      // 2^-level, exactly what (float)(1. / (1 << level)) gives
         float px = prevx * lscale, py = prevy * lscale;
         float nx, ny;
         if (level == P.nlevels - 1) { nx = nxp * lscale; ny = nyp * lscale; }
@@ -330,7 +330,7 @@ __device__ __forceinline__ int lk_pyramid(WarpSmem<WIN> &ws, uint32_t &phase, co
                     const int x11 = (short)(db1 & 0xFFFFu), y11 = (int)db1 >> 16;
                     int ix = (x00 * iw00 + x01 * iw01 + x10 * iw10 + x11 * iw11 + (1 << 13)) >> 14;
                     int iy = (y00 * iw00 + y01 * iw01 + y10 * iw10 + y11 * iw11 + (1 << 13)) >> 14;
-                    const bool ok = ivalid[r] && (iseg[r] * SEG + k < WIN);
+                    const bool ok = ivalid[r] && (SEG * NSEG == WIN || iseg[r] * SEG + k < WIN);   // 21 = 3 x 7: no partial segment
                     if (!ok) { ix = 0; iy = 0; }
                     Cv[r][k] = 256 - (iv[k] << 9);
                     if constexpr (C::PACKED) Ixv[r][k] = (iy << 16) | (ix & 0xFFFF);
