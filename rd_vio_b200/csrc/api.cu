@@ -173,7 +173,7 @@ static int stage_sources(rdfe_ctx *ctx, const int *slots, int n, const uint8_t *
 }
 
 static int sync_all_streams(rdfe_ctx *ctx) {
-    for (cudaStream_t st : {ctx->stream, ctx->aux_stream, ctx->aux_stream2, ctx->pre_stream, ctx->sel_stream[0], ctx->sel_stream[1],
+    for (cudaStream_t st : {ctx->stream, ctx->aux_stream, ctx->aux_stream2, ctx->pre_stream, ctx->pre_stream2, ctx->sel_stream[0], ctx->sel_stream[1],
                             ctx->trk_stream, ctx->post_stream})
         RDFE_CUDA_OK(cudaStreamSynchronize(st));
     return RDFE_OK;
@@ -372,6 +372,8 @@ int rdfe_create(const rdfe_config *cfg, rdfe_ctx **out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CK(cudaStreamCreateWithPriority(&ctx->pre_stream, cudaStreamNonBlocking, pre_prio));
+    CK(cudaStreamCreateWithPriority(&ctx->pre_stream2, cudaStreamNonBlocking, pre_prio));
+    CK(cudaEventCreateWithFlags(&ctx->ev_sc0_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_apply_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_pre_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_step_done[0], cudaEventDisableTiming));
@@ -448,6 +450,8 @@ void rdfe_destroy(rdfe_ctx *ctx) {
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->pre_stream) { cudaStreamSynchronize(ctx->pre_stream); cudaStreamDestroy(ctx->pre_stream); }
+    if (ctx->pre_stream2) { cudaStreamSynchronize(ctx->pre_stream2); cudaStreamDestroy(ctx->pre_stream2); }
+    if (ctx->ev_sc0_done) cudaEventDestroy(ctx->ev_sc0_done);
     if (ctx->ev_apply_done) cudaEventDestroy(ctx->ev_apply_done);
     if (ctx->ev_pre_done) cudaEventDestroy(ctx->ev_pre_done);
     for (int p = 0; p < 2; ++p) if (ctx->ev_step_done[p]) cudaEventDestroy(ctx->ev_step_done[p]);
@@ -874,7 +878,21 @@ int rdfe_frontend_step_dev(rdfe_ctx *ctx, const int *prev_slots, const int *new_
         cudaEventRecord(ctx->ev_clahe_ring[ctx->step_index & 3], ps);
         for (int i = 0; i < n; ++i) ctx->slot_clahe_step[new_slots[i]] = (long long)ctx->step_index;
         cudaEventRecord(ctx->ev_apply_done, ps);
-        rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
+        // The preprocess chain is the longest dependent chain of the pipelined step (its small kernels wait for SM slots
+        // beside LK and Harris).  Scharr of level 0 -- 3/4 of the derivative work -- needs only the CLAHE output, so it runs
+        // on a second preprocess stream beside the pyrDown chain; the small levels' Scharr follows the last pyrDown.
+        static const int s_split = [] { const char *e = getenv("RDFE_SCHARR_SPLIT"); return e ? atoi(e) : 1; }();
+        if (s_split && ctx->pyr.nlevels > 1) {
+            cudaStreamWaitEvent(ctx->pre_stream2, ctx->ev_apply_done, 0);
+            ctx->ls = ctx->pre_stream2;
+            rc = check_launch(ctx, launch_scharr_levels(ctx, sn, 0, 1), "scharr0");
+            cudaEventRecord(ctx->ev_sc0_done, ctx->pre_stream2);
+            ctx->ls = ps;
+            if (rc == RDFE_OK) rc = check_launch(ctx, launch_pyrdowns(ctx, sn), "pyrdown");
+            if (rc == RDFE_OK) rc = check_launch(ctx, launch_scharr_levels(ctx, sn, 1, ctx->pyr.nlevels), "scharr1");
+            cudaStreamWaitEvent(ps, ctx->ev_sc0_done, 0);
+        } else
+            rc = check_launch(ctx, launch_pyramid(ctx, sn), "pyramid");
         if (rc) { restore_p(); return rc; }
         cudaEventRecord(ctx->ev_pre_done, ps);
         // detection branch

@@ -219,6 +219,8 @@ struct rdfe_ctx {
     // cross-step pipelining (rdfe_set_pipelining): preprocess of step s+1 on pre_stream beside track/detect of step s
     bool pipeline_steps;
     cudaStream_t pre_stream;
+    cudaStream_t pre_stream2;     // Scharr of level 0 beside the pyrDown chain (pipelined step)
+    cudaEvent_t ev_sc0_done;
     cudaEvent_t ev_apply_done, ev_pre_done, ev_step_done[2];
     int64_t step_index;
     uint8_t *last_step_slots;     // [num_slots] 1 = touched by the previous step
@@ -306,6 +308,8 @@ inline void prof_end(rdfe_ctx *ctx, int i) {
 int launch_clahe(rdfe_ctx *ctx, const SlotList &slots, const uint8_t *const *d_src, size_t src_pitch,
                  int src_vec4, const ClaheParams &cp);
 int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots);
+int launch_pyrdowns(rdfe_ctx *ctx, const SlotList &slots);
+int launch_scharr_levels(rdfe_ctx *ctx, const SlotList &slots, int lo, int hi);
 int launch_harris_candidates(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p,
                              float *d_response /* optional [n][H][W] */);
 int launch_select(rdfe_ctx *ctx, const SlotList &slots, const rdfe_detect_params &p, double *d_xy, int *d_counts,

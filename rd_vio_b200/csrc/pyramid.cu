@@ -185,7 +185,7 @@ scharr_kernel(Pyramid pyr, SlotList slots, ItemTable tt) {
     }
 }
 
-int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
+int launch_pyrdowns(rdfe_ctx *ctx, const SlotList &slots) {
     const Pyramid &pyr = ctx->pyr;
     int launches = 0;
     for (int l = 0; l + 1 < pyr.nlevels; ++l) {
@@ -198,17 +198,29 @@ int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
         RDFE_LAUNCH(ctx, K_PYRDOWN, (pyrdown_kernel<<<grid, PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, l, tiles_x, n_items, pd_rows)));
         ++launches;
     }
+    return launches;
+}
+
+// Scharr derivatives of levels [lo, hi) in one launch (levels outside the range get no work items)
+int launch_scharr_levels(rdfe_ctx *ctx, const SlotList &slots, int lo, int hi) {
+    const Pyramid &pyr = ctx->pyr;
     ItemTable tt;
     tt.base[0] = 0;
     for (int l = 0; l < pyr.nlevels; ++l) {
         const LevelGeom &g = pyr.lv[l];
         tt.tiles_x[l] = (g.w + 127) / 128;
         tt.rows[l] = adaptive_strip_rows(g.h, tt.tiles_x[l] * slots.n, 4, SC_ROWS);
-        tt.first[l] = tt.tiles_x[l] * ((g.h + tt.rows[l] - 1) / tt.rows[l]);      // work items (warps) of level l per image
+        tt.first[l] = (l >= lo && l < hi) ? tt.tiles_x[l] * ((g.h + tt.rows[l] - 1) / tt.rows[l]) : 0;   // work items (warps) of level l per image
         tt.base[l + 1] = tt.base[l] + tt.first[l] * slots.n;
     }
+    if (tt.base[pyr.nlevels] == 0) return 0;
     RDFE_LAUNCH(ctx, K_SCHARR, (scharr_kernel<<<(tt.base[pyr.nlevels] + PW_WARPS - 1) / PW_WARPS, PW_WARPS * 32, 0, ctx->ls>>>(pyr, slots, tt)));
-    return launches + 1;
+    return 1;
+}
+
+int launch_pyramid(rdfe_ctx *ctx, const SlotList &slots) {
+    const int a = launch_pyrdowns(ctx, slots);
+    return a + launch_scharr_levels(ctx, slots, 0, ctx->pyr.nlevels);
 }
 
 }  // namespace rdfe
