@@ -466,7 +466,9 @@ def measure_gpu(args, env, wl_name, S, T, steps, warmup, profile_steps, want_e2e
 
         h2d = S * H * W + 2 * S * stride * 16 + 2 * S * 4
         d2h = S * stride * 16 + S * 4 + S * stride + 4
-        e_steps = max(10, min(steps, 200))
+        # the end-to-end leg always times at least 100 steps: with the driver's small K the fill and drain of the three-deep
+        # pipeline (about two steps) would otherwise weigh 10 % of the timed region
+        e_steps = min(max(steps, 100), 400)
         def run_pipelined(nsteps, tt):       # up to three steps in flight (rdfe_frontend_step_submit's pipeline depth)
             pending = []
             for _ in range(nsteps):
