@@ -1033,7 +1033,7 @@ int rdfe_set_pipelining(rdfe_ctx *ctx, int on) {
     return RDFE_OK;
 }
 
-// ------------------------------------- pipelined host-buffer step (2 stages)
+// ------------------------------------- pipelined host-buffer step (kPipeDepth = 3 stages)
 // submit(t+1) may be called before wait(t): the frames of step t+1 are uploaded on a copy stream while the
 // kernels of step t run; results come back through pinned staging and are handed out by wait().
 int rdfe_frontend_step_submit(rdfe_ctx *ctx, const int *prev_slots, const int *new_slots, int n,
