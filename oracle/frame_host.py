@@ -1,4 +1,5 @@
-"""Host-side mirror of the callers of the Image plugin:
+"""TEST INFRASTRUCTURE ONLY (lives beside the oracle; the product package never imports it).
+Host-side mirror of the callers of the Image plugin:
 
   Frame::detect_keypoints / Frame::track_keypoints   /root/reference/src/rdvio_map/src/frame.cpp:55-172
   apply_k / remove_k                                  src/rdvio_geometry/include/rdvio/geometry/stereo.h:7-14
